@@ -1,0 +1,67 @@
+"""ctypes binding of libfa_b200.so -- exactly the symbols include/fa_b200.h declares."""
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_NAME = "libfa_b200.so"
+_lock = threading.Lock()
+_lib = None
+
+c_void_p, c_int, c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+c_float_p = ctypes.c_void_p  # device / host addresses are passed as integers
+
+# name -> (restype, argtypes); kept in sync with include/fa_b200.h (tests/test_abi.py checks it)
+SIGNATURES = {
+    "fa_version": (c_int, []),
+    "fa_strerror": (ctypes.c_char_p, [c_int]),
+    "fa_forward": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_float, c_void_p]),
+    "fa_forward_f32out": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_float, c_void_p]),
+    "fa_forward_partial": (c_int, [c_void_p] * 6 + [c_int] * 5 + [c_float, c_int, c_int, c_void_p, c_void_p]),
+    "gemm_fused_epilogue": (c_int, [c_void_p] * 5 + [c_int] * 3 + [c_void_p]),
+    "softmax_rows": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "fa_forward_host": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_float]),
+    "gemm_fused_epilogue_host": (c_int, [c_void_p] * 5 + [c_int] * 3),
+    "softmax_rows_host": (c_int, [c_void_p, c_void_p, c_int, c_int]),
+    "fa_host_release": (c_int, []),
+    "fa_last_debug": (c_int, [ctypes.POINTER(ctypes.c_uint), c_int]),
+    "fa_launch_count": (ctypes.c_ulonglong, []),
+}
+
+
+class FaError(RuntimeError):
+    """A non-zero return code from the C ABI (negative: FA_ERR_*, positive: cudaError_t)."""
+
+    def __init__(self, code, what, message):
+        super().__init__(f"{what} failed with code {code}: {message}")
+        self.code = code
+
+
+def lib_path():
+    return os.path.join(_HERE, _LIB_NAME)
+
+
+def load_library():
+    """Load the CUDA library.  Raises (never falls back) when it has not been built."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = lib_path()
+        if not os.path.exists(path):
+            raise FileNotFoundError(
+                f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  This package has no CPU fallback.")
+        lib = ctypes.CDLL(path, mode=ctypes.RTLD_LOCAL)
+        for name, (restype, argtypes) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the library lacks a declared symbol
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = lib
+        return lib
+
+
+def check(code, what):
+    if code != 0:
+        msg = load_library().fa_strerror(code)
+        raise FaError(code, what, msg.decode() if msg else "?")

@@ -1,0 +1,456 @@
+// C-ABI entry points (include/fa_b200.h) and the thin C++ host layer behind them: argument
+// validation, CUtensorMap construction, shared-memory opt-in, launch.  No dispatch table, no CPU
+// fallback: on anything but an sm_100 device the compute entry points return FA_ERR_NO_DEVICE.
+//
+// The reference's host side is a main() per program (constexpr sizes -> cudaMalloc -> H2D ->
+// <<<>>> on the default stream -> D2H, e.g. flashattn_warp_spc/flashattn_streaming_16x32_2warp_softmax_v12i.cu:298-393)
+// that aborts through CHECK_CUDA (:21-29).  Here the same flow is behind *_host entry points and
+// every failure is a return code.
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/fa_b200.h"
+#include "fa_fwd.cuh"
+#include "gemm_fused.cuh"
+#include "softmax_rows.cuh"
+
+namespace {
+
+using namespace fa;
+
+constexpr int kMaxDevices = 64;
+std::atomic<unsigned long long> g_launches{0};
+
+// ---- driver entry point: cuTensorMapEncodeTiled without linking libcuda -----------------
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_fn() {
+  static std::once_flag once;
+  static EncodeTiledFn fn = nullptr;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  return fn;
+}
+
+// rank-2/3 tiled map over a row-major tensor whose innermost extent is dims[0]; 128B swizzle.
+int make_map(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, const void* base, int rank,
+             const uint64_t* dims, const uint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return FA_ERR_DRIVER_ENTRY;
+  cuuint64_t gdim[3];
+  cuuint64_t gstride[2];
+  cuuint32_t bdim[3];
+  cuuint32_t estride[3] = {1, 1, 1};
+  uint64_t pitch = static_cast<uint64_t>(elem_bytes);
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    pitch *= dims[i];
+    if (i < rank - 1) gstride[i] = pitch;
+  }
+  const CUresult r = fn(map, dt, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim, gstride, bdim, estride,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? FA_OK : FA_ERR_DRIVER_ENTRY;
+}
+
+// ---- per-device state -------------------------------------------------------------------
+struct DeviceState {
+  bool probed = false;
+  bool is_sm100 = false;
+  int sm_count = 0;
+  bool attr_fa64 = false, attr_fa128 = false, attr_gemm = false;
+  // scratch for the *_host entry points
+  void* scratch[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t scratch_bytes[6] = {0, 0, 0, 0, 0, 0};
+};
+DeviceState g_dev[kMaxDevices];
+std::mutex g_mutex;
+unsigned int* g_dbg_host = nullptr;  // mapped pinned page shared by all devices
+
+int current_device_state(DeviceState** out) {
+  int dev = -1;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return FA_ERR_NO_DEVICE;
+  }
+  if (dev < 0 || dev >= kMaxDevices) return FA_ERR_NO_DEVICE;
+  std::lock_guard<std::mutex> lock(g_mutex);
+  DeviceState& st = g_dev[dev];
+  if (!st.probed) {
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return FA_ERR_NO_DEVICE;
+    }
+    cudaDeviceGetAttribute(&st.sm_count, cudaDevAttrMultiProcessorCount, dev);
+    st.is_sm100 = (major == 10);
+    st.probed = true;
+  }
+  if (!st.is_sm100) return FA_ERR_NO_DEVICE;
+  if (g_dbg_host == nullptr) {
+    void* ptr = nullptr;
+    if (cudaHostAlloc(&ptr, 256, cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess) {
+      std::memset(ptr, 0, 256);
+      g_dbg_host = static_cast<unsigned int*>(ptr);
+    } else {
+      (void)cudaGetLastError();
+    }
+  }
+  *out = &st;
+  return FA_OK;
+}
+
+DebugChannel debug_channel() {
+  DebugChannel d;
+  d.words = nullptr;
+  if (g_dbg_host != nullptr) {
+    void* dptr = nullptr;
+    if (cudaHostGetDevicePointer(&dptr, g_dbg_host, 0) == cudaSuccess)
+      d.words = static_cast<unsigned int*>(dptr);
+    else
+      (void)cudaGetLastError();
+  }
+  return d;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+template <typename Kernel>
+int ensure_smem_attr(bool* done, Kernel kernel, int bytes) {
+  if (*done) return FA_OK;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  *done = true;
+  return FA_OK;
+}
+
+// ---- attention ----------------------------------------------------------------------------
+struct FaCall {
+  const void *Q, *K, *V;
+  void* O16;       // fp16 output (F16 mode, or STATE + is_last)
+  float* O32;      // F32 output or O_acc
+  float *m, *l;
+  int B, H, Nq, Nkv, D;
+  float scale;
+  int mode, is_first, is_last;
+};
+
+template <int D>
+int launch_fa(DeviceState* st, const FaCall& c, cudaStream_t stream) {
+  using Cfg = FaCfg<D>;
+  const uint64_t BH = static_cast<uint64_t>(c.B) * c.H;
+  CUtensorMap mq, mk, mv, mo;
+  const uint32_t box[3] = {64, 128, 1};
+  const uint64_t dq[3] = {static_cast<uint64_t>(D), static_cast<uint64_t>(c.Nq), BH};
+  const uint64_t dk[3] = {static_cast<uint64_t>(D), static_cast<uint64_t>(c.Nkv), BH};
+  int rc;
+  if ((rc = make_map(&mq, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, c.Q, 3, dq, box)) != FA_OK) return rc;
+  if ((rc = make_map(&mk, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, c.K, 3, dk, box)) != FA_OK) return rc;
+  if ((rc = make_map(&mv, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, c.V, 3, dk, box)) != FA_OK) return rc;
+  if (c.O16 != nullptr) {
+    if ((rc = make_map(&mo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, c.O16, 3, dq, box)) != FA_OK) return rc;
+  } else {
+    mo = mq;  // never dereferenced in the modes that pass no fp16 output
+  }
+  bool* flag = (D == 64) ? &st->attr_fa64 : &st->attr_fa128;
+  {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if ((rc = ensure_smem_attr(flag, fa_fwd_kernel<D>, Cfg::kSmemBytes)) != FA_OK) return rc;
+  }
+  FaParams p;
+  p.nq = c.Nq;
+  p.nkv = c.Nkv;
+  p.q_blocks = (c.Nq + 255) / 256;
+  float sl2 = c.scale * 1.4426950408889634f;
+  if (fabsf(sl2) < 1e-30f) sl2 = (sl2 < 0.f || (sl2 == 0.f && std::signbit(sl2))) ? -1e-30f : 1e-30f;
+  p.scale_log2 = sl2;
+  p.mode = c.mode;
+  p.is_first = c.is_first;
+  p.is_last = c.is_last;
+  p.o_f32 = c.O32;
+  p.m_state = c.m;
+  p.l_state = c.l;
+  p.dbg = debug_channel();
+  const uint64_t grid = BH * static_cast<uint64_t>(p.q_blocks);
+  if (grid == 0 || grid > 0x7fffffffull) return FA_ERR_BAD_SHAPE;
+  fa_fwd_kernel<D><<<static_cast<unsigned>(grid), Cfg::kThreads, Cfg::kSmemBytes, stream>>>(mq, mk, mv, mo, p);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  const cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? FA_OK : static_cast<int>(e);
+}
+
+int run_fa(const FaCall& c, void* stream) {
+  if (c.B <= 0 || c.H <= 0 || c.Nq <= 0 || c.Nkv <= 0) return FA_ERR_BAD_SHAPE;
+  if (c.D != 64 && c.D != 128) return FA_ERR_BAD_HEAD_DIM;
+  if (!(c.scale == c.scale) || std::isinf(c.scale)) return FA_ERR_BAD_ARGUMENT;
+  if (c.Q == nullptr || c.K == nullptr || c.V == nullptr) return FA_ERR_NULL_POINTER;
+  if (c.mode == FA_MODE_F16 && c.O16 == nullptr) return FA_ERR_NULL_POINTER;
+  if (c.mode == FA_MODE_F32 && c.O32 == nullptr) return FA_ERR_NULL_POINTER;
+  if (c.mode == FA_MODE_STATE) {
+    if (c.O32 == nullptr || c.m == nullptr || c.l == nullptr) return FA_ERR_NULL_POINTER;
+    if (c.is_last && c.O16 == nullptr) return FA_ERR_NULL_POINTER;
+    if (!aligned16(c.m) || !aligned16(c.l)) return FA_ERR_MISALIGNED;
+  }
+  if (!aligned16(c.Q) || !aligned16(c.K) || !aligned16(c.V) || !aligned16(c.O16) || !aligned16(c.O32))
+    return FA_ERR_MISALIGNED;
+  const uint64_t BH = static_cast<uint64_t>(c.B) * c.H;
+  if (BH > 0x7fffffffull) return FA_ERR_BAD_SHAPE;
+  DeviceState* st = nullptr;
+  int rc = current_device_state(&st);
+  if (rc != FA_OK) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return c.D == 64 ? launch_fa<64>(st, c, s) : launch_fa<128>(st, c, s);
+}
+
+// ---- GEMM ---------------------------------------------------------------------------------
+int run_gemm(const void* A, const void* Bm, const float* bias, const float* residual, float* C, int M, int N, int K,
+             void* stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return FA_ERR_BAD_SHAPE;
+  if (A == nullptr || Bm == nullptr || C == nullptr) return FA_ERR_NULL_POINTER;
+  if ((N & 7) != 0 || (K & 7) != 0) return FA_ERR_MISALIGNED;
+  if (!aligned16(A) || !aligned16(Bm) || !aligned16(C) || !aligned16(bias) || !aligned16(residual))
+    return FA_ERR_MISALIGNED;
+  DeviceState* st = nullptr;
+  int rc = current_device_state(&st);
+  if (rc != FA_OK) return rc;
+  CUtensorMap ma, mb;
+  const uint64_t da[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
+  const uint32_t ba[2] = {64, 128};
+  const uint64_t db[2] = {static_cast<uint64_t>(N), static_cast<uint64_t>(K)};
+  const uint32_t bb[2] = {64, 64};
+  if ((rc = make_map(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, A, 2, da, ba)) != FA_OK) return rc;
+  if ((rc = make_map(&mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, Bm, 2, db, bb)) != FA_OK) return rc;
+  {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if ((rc = ensure_smem_attr(&st->attr_gemm, gemm_fused_kernel, GemmCfg::kSmemBytes)) != FA_OK) return rc;
+  }
+  GemmParams p;
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.m_blocks = (M + GemmCfg::kBM - 1) / GemmCfg::kBM;
+  p.n_blocks = (N + GemmCfg::kBN - 1) / GemmCfg::kBN;
+  p.bias = bias;
+  p.residual = residual;
+  p.C = C;
+  p.dbg = debug_channel();
+  const long long tiles = static_cast<long long>(p.m_blocks) * p.n_blocks;
+  if (tiles > 0x7fffffffll) return FA_ERR_BAD_SHAPE;
+  const int grid = static_cast<int>(tiles < st->sm_count ? tiles : st->sm_count);
+  gemm_fused_kernel<<<grid, GemmCfg::kThreads, GemmCfg::kSmemBytes, static_cast<cudaStream_t>(stream)>>>(ma, mb, p);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  const cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? FA_OK : static_cast<int>(e);
+}
+
+// ---- softmax ------------------------------------------------------------------------------
+template <int TPR, int V4>
+void launch_softmax_reg(const float* X, float* P, int rows, int N, int sm_count, cudaStream_t s) {
+  constexpr int kGroups = 256 / TPR;
+  long long ctas = (static_cast<long long>(rows) + kGroups - 1) / kGroups;
+  const long long cap = static_cast<long long>(sm_count) * 8;  // up to 8 resident CTAs per SM, grid-stride beyond
+  if (ctas > cap) ctas = cap;
+  softmax_rows_reg_kernel<TPR, V4><<<static_cast<unsigned>(ctas), 256, 0, s>>>(X, P, rows, N);
+}
+
+int run_softmax(const float* X, float* P, int rows, int N, void* stream) {
+  if (rows <= 0 || N <= 0) return FA_ERR_BAD_SHAPE;
+  if (X == nullptr || P == nullptr) return FA_ERR_NULL_POINTER;
+  if ((reinterpret_cast<uintptr_t>(X) & 3u) || (reinterpret_cast<uintptr_t>(P) & 3u)) return FA_ERR_MISALIGNED;
+  DeviceState* st = nullptr;
+  int rc = current_device_state(&st);
+  if (rc != FA_OK) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool vec_ok = (N % 4 == 0) && aligned16(X) && aligned16(P);
+  const int sm = st->sm_count;
+  if (vec_ok && N <= 128) launch_softmax_reg<32, 1>(X, P, rows, N, sm, s);
+  else if (vec_ok && N <= 256) launch_softmax_reg<32, 2>(X, P, rows, N, sm, s);
+  else if (vec_ok && N <= 512) launch_softmax_reg<32, 4>(X, P, rows, N, sm, s);
+  else if (vec_ok && N <= 1024) launch_softmax_reg<32, 8>(X, P, rows, N, sm, s);
+  else if (vec_ok && N <= 2048) launch_softmax_reg<256, 2>(X, P, rows, N, sm, s);
+  else if (vec_ok && N <= 4096) launch_softmax_reg<256, 4>(X, P, rows, N, sm, s);
+  else if (vec_ok && N <= 8192) launch_softmax_reg<256, 8>(X, P, rows, N, sm, s);
+  else {
+    long long ctas = rows;
+    const long long cap = static_cast<long long>(sm) * 8;
+    if (ctas > cap) ctas = cap;
+    softmax_rows_3pass_kernel<<<static_cast<unsigned>(ctas), 256, 0, s>>>(X, P, rows, N);
+  }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  const cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? FA_OK : static_cast<int>(e);
+}
+
+// ---- host-buffer variants -----------------------------------------------------------------
+int scratch_get(DeviceState* st, int slot, size_t bytes, void** out) {
+  if (st->scratch_bytes[slot] < bytes) {
+    if (st->scratch[slot] != nullptr) cudaFree(st->scratch[slot]);
+    st->scratch[slot] = nullptr;
+    st->scratch_bytes[slot] = 0;
+    cudaError_t e = cudaMalloc(&st->scratch[slot], bytes);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    st->scratch_bytes[slot] = bytes;
+  }
+  *out = st->scratch[slot];
+  return FA_OK;
+}
+
+#define FA_CUDA_TRY(expr)                               \
+  do {                                                  \
+    cudaError_t e__ = (expr);                           \
+    if (e__ != cudaSuccess) return static_cast<int>(e__); \
+  } while (0)
+
+}  // namespace
+
+// =========================================== C ABI ==========================================
+extern "C" {
+
+int fa_version(void) { return 100; }
+
+const char* fa_strerror(int code) {
+  switch (code) {
+    case FA_OK: return "ok";
+    case FA_ERR_BAD_SHAPE: return "bad shape (non-positive extent or index overflow)";
+    case FA_ERR_BAD_HEAD_DIM: return "head dim must be 64 or 128";
+    case FA_ERR_MISALIGNED: return "pointer or row pitch not 16-byte aligned";
+    case FA_ERR_NULL_POINTER: return "required pointer is null";
+    case FA_ERR_NO_DEVICE: return "current device is not an sm_100 (B200) GPU; there is no CPU fallback";
+    case FA_ERR_DRIVER_ENTRY: return "cuTensorMapEncodeTiled unavailable or failed";
+    case FA_ERR_BAD_ARGUMENT: return "bad argument";
+    default: break;
+  }
+  if (code > 0) return cudaGetErrorString(static_cast<cudaError_t>(code));
+  return "unknown error";
+}
+
+int fa_forward(const void* Q, const void* K, const void* V, void* O, int B, int H, int N, int D, float scale,
+               void* stream) {
+  FaCall c{Q, K, V, O, nullptr, nullptr, nullptr, B, H, N, N, D, scale, FA_MODE_F16, 1, 1};
+  return run_fa(c, stream);
+}
+
+int fa_forward_f32out(const void* Q, const void* K, const void* V, float* O, int B, int H, int N, int D, float scale,
+                      void* stream) {
+  FaCall c{Q, K, V, nullptr, O, nullptr, nullptr, B, H, N, N, D, scale, FA_MODE_F32, 1, 1};
+  return run_fa(c, stream);
+}
+
+int fa_forward_partial(const void* Q, const void* K, const void* V, float* O_acc, float* m, float* l, int B, int H,
+                       int Nq, int Nkv, int D, float scale, int is_first, int is_last, void* O_final, void* stream) {
+  FaCall c{Q, K, V, is_last ? O_final : nullptr, O_acc, m, l, B, H, Nq, Nkv, D, scale, FA_MODE_STATE,
+           is_first ? 1 : 0, is_last ? 1 : 0};
+  return run_fa(c, stream);
+}
+
+int gemm_fused_epilogue(const void* A, const void* Bm, const float* bias, const float* residual, float* C, int M,
+                        int N, int K, void* stream) {
+  return run_gemm(A, Bm, bias, residual, C, M, N, K, stream);
+}
+
+int softmax_rows(const float* X, float* P, int rows, int N, void* stream) { return run_softmax(X, P, rows, N, stream); }
+
+int fa_forward_host(const void* Q, const void* K, const void* V, void* O, int B, int H, int N, int D, float scale) {
+  if (B <= 0 || H <= 0 || N <= 0) return FA_ERR_BAD_SHAPE;
+  if (D != 64 && D != 128) return FA_ERR_BAD_HEAD_DIM;
+  if (Q == nullptr || K == nullptr || V == nullptr || O == nullptr) return FA_ERR_NULL_POINTER;
+  DeviceState* st = nullptr;
+  int rc = current_device_state(&st);
+  if (rc != FA_OK) return rc;
+  const size_t bytes = static_cast<size_t>(B) * H * N * D * 2;
+  void *dq, *dk, *dv, *dout;
+  if ((rc = scratch_get(st, 0, bytes, &dq)) != FA_OK) return rc;
+  if ((rc = scratch_get(st, 1, bytes, &dk)) != FA_OK) return rc;
+  if ((rc = scratch_get(st, 2, bytes, &dv)) != FA_OK) return rc;
+  if ((rc = scratch_get(st, 3, bytes, &dout)) != FA_OK) return rc;
+  FA_CUDA_TRY(cudaMemcpyAsync(dq, Q, bytes, cudaMemcpyHostToDevice, 0));
+  FA_CUDA_TRY(cudaMemcpyAsync(dk, K, bytes, cudaMemcpyHostToDevice, 0));
+  FA_CUDA_TRY(cudaMemcpyAsync(dv, V, bytes, cudaMemcpyHostToDevice, 0));
+  if ((rc = fa_forward(dq, dk, dv, dout, B, H, N, D, scale, nullptr)) != FA_OK) return rc;
+  FA_CUDA_TRY(cudaMemcpyAsync(O, dout, bytes, cudaMemcpyDeviceToHost, 0));
+  FA_CUDA_TRY(cudaStreamSynchronize(0));
+  return FA_OK;
+}
+
+int gemm_fused_epilogue_host(const void* A, const void* Bm, const float* bias, const float* residual, float* C, int M,
+                             int N, int K) {
+  if (M <= 0 || N <= 0 || K <= 0) return FA_ERR_BAD_SHAPE;
+  if (A == nullptr || Bm == nullptr || C == nullptr) return FA_ERR_NULL_POINTER;
+  DeviceState* st = nullptr;
+  int rc = current_device_state(&st);
+  if (rc != FA_OK) return rc;
+  const size_t ab = static_cast<size_t>(M) * K * 2, bb = static_cast<size_t>(K) * N * 2;
+  const size_t cb = static_cast<size_t>(M) * N * 4, biasb = static_cast<size_t>(N) * 4;
+  void *da, *db, *dbias = nullptr, *dres = nullptr, *dc;
+  if ((rc = scratch_get(st, 0, ab, &da)) != FA_OK) return rc;
+  if ((rc = scratch_get(st, 1, bb, &db)) != FA_OK) return rc;
+  if ((rc = scratch_get(st, 3, cb, &dc)) != FA_OK) return rc;
+  FA_CUDA_TRY(cudaMemcpyAsync(da, A, ab, cudaMemcpyHostToDevice, 0));
+  FA_CUDA_TRY(cudaMemcpyAsync(db, Bm, bb, cudaMemcpyHostToDevice, 0));
+  if (bias != nullptr) {
+    if ((rc = scratch_get(st, 4, biasb, &dbias)) != FA_OK) return rc;
+    FA_CUDA_TRY(cudaMemcpyAsync(dbias, bias, biasb, cudaMemcpyHostToDevice, 0));
+  }
+  if (residual != nullptr) {
+    if ((rc = scratch_get(st, 2, cb, &dres)) != FA_OK) return rc;
+    FA_CUDA_TRY(cudaMemcpyAsync(dres, residual, cb, cudaMemcpyHostToDevice, 0));
+  }
+  if ((rc = gemm_fused_epilogue(da, db, static_cast<const float*>(dbias), static_cast<const float*>(dres),
+                                static_cast<float*>(dc), M, N, K, nullptr)) != FA_OK)
+    return rc;
+  FA_CUDA_TRY(cudaMemcpyAsync(C, dc, cb, cudaMemcpyDeviceToHost, 0));
+  FA_CUDA_TRY(cudaStreamSynchronize(0));
+  return FA_OK;
+}
+
+int softmax_rows_host(const float* X, float* P, int rows, int N) {
+  if (rows <= 0 || N <= 0) return FA_ERR_BAD_SHAPE;
+  if (X == nullptr || P == nullptr) return FA_ERR_NULL_POINTER;
+  DeviceState* st = nullptr;
+  int rc = current_device_state(&st);
+  if (rc != FA_OK) return rc;
+  const size_t bytes = static_cast<size_t>(rows) * N * 4;
+  void* dx;
+  if ((rc = scratch_get(st, 0, bytes, &dx)) != FA_OK) return rc;
+  FA_CUDA_TRY(cudaMemcpyAsync(dx, X, bytes, cudaMemcpyHostToDevice, 0));
+  if ((rc = softmax_rows(static_cast<const float*>(dx), static_cast<float*>(dx), rows, N, nullptr)) != FA_OK) return rc;
+  FA_CUDA_TRY(cudaMemcpyAsync(P, dx, bytes, cudaMemcpyDeviceToHost, 0));
+  FA_CUDA_TRY(cudaStreamSynchronize(0));
+  return FA_OK;
+}
+
+int fa_host_release(void) {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) {
+    (void)cudaGetLastError();
+    return FA_ERR_NO_DEVICE;
+  }
+  DeviceState& st = g_dev[dev];
+  for (int i = 0; i < 6; ++i) {
+    if (st.scratch[i] != nullptr) cudaFree(st.scratch[i]);
+    st.scratch[i] = nullptr;
+    st.scratch_bytes[i] = 0;
+  }
+  return FA_OK;
+}
+
+int fa_last_debug(unsigned int* words, int n) {
+  if (words == nullptr || n <= 0 || g_dbg_host == nullptr) return 0;
+  const int k = n < 8 ? n : 8;
+  for (int i = 0; i < k; ++i) words[i] = reinterpret_cast<volatile unsigned int*>(g_dbg_host)[i];
+  return k;
+}
+
+unsigned long long fa_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+}  // extern "C"

@@ -1,0 +1,471 @@
+// Non-causal FlashAttention forward for sm_100a: TMA -> swizzled smem ring -> tcgen05.mma with
+// S and O accumulators in TMEM -> one-thread-per-row exp2-domain online softmax read out of TMEM
+// -> lazy O rescale in a correction warpgroup -> normalise -> TMA store.
+//
+// Replaces the reference's general tensor-core kernels
+//   flashattn_forward_wmma_v5_cp_async_kernel
+//     (FlashAttention/flashattn_forward_memory_bound/flashattn_forward_wmma_v5_cp_async.cu:99-459)
+//   flashattn_forward_wmma_v4_kernel (FlashAttention/flashattn_forward_wmma/flashattn_forward_wmma_v4.cu:52-413)
+// which use 32x32 WMMA tiles, cp.async.cg 2-stage K/V ping-pong and 8 + D/32 __syncthreads per
+// 32-key tile.  Mapping of subsystems:
+//   K/V loader  : cp.async + wait_group 0 + __syncthreads (v5:229-256)  -> one thread issuing
+//                 cp.async.bulk.tensor into a STAGES-deep 128B-swizzled ring, full/empty mbarriers
+//   contractions: wmma 16x16x16 via smem round trips (v4:197-234,339-400) -> tcgen05.mma
+//                 128x128x16 (QK^T, both operands smem) and 128xDx16 (PV, P read from TMEM, V
+//                 as an MN-major smem operand so no transposition is needed)
+//   softmax     : warp-shuffle row reductions / lanes<32 scalar loop (v4:237-300, v5:312-348) ->
+//                 tcgen05.ld 32x32b gives each thread one whole row: no shuffles at all
+//   rescale     : O_smem *= alpha every tile (v5:352-360) -> only when the running max grows by
+//                 more than 2^8 (lazy), done by a dedicated correction warpgroup on TMEM
+//   epilogue    : scalar fp32 stores (v4:403-412) -> 1/l in registers, fp16, swizzled smem, TMA store
+//
+// CTA = 512 threads = 4 warpgroups, one CTA per SM, 256 query rows per CTA as two 128-row tiles
+// that ping-pong on the tensor pipe:
+//   WG0 (warps 0-3)   softmax of Q tile 0        WG1 (warps 4-7)  softmax of Q tile 1
+//   WG2 (warps 8-11)  correction + epilogue      WG3: warp 12 = MMA issuer (1 thread),
+//                                                     warp 13 = TMA producer (1 thread)
+// TMEM (512 columns x 128 lanes x 32 bit): S0 @0, S1 @128, O0 @256, O1 @256+D.  P (fp16, two per
+// column) overwrites the first 64 columns of its own S.
+#pragma once
+#include "sm100_ptx.cuh"
+
+namespace fa {
+
+enum FaMode : int { FA_MODE_F16 = 0, FA_MODE_F32 = 1, FA_MODE_STATE = 2 };
+
+struct FaParams {
+  int nq;            // query rows per (b,h)
+  int nkv;           // key/value rows per (b,h)
+  int q_blocks;      // ceil(nq / 256)
+  float scale_log2;  // scale * log2(e)
+  int mode;          // FaMode
+  int is_first;      // FA_MODE_STATE: incoming state is empty
+  int is_last;       // FA_MODE_STATE: also emit normalised fp16 through mapO
+  float* o_f32;      // FA_MODE_F32: [bh, nq, D] normalised;  FA_MODE_STATE: un-normalised O_acc
+  float* m_state;    // FA_MODE_STATE: [bh, nq]  running max of scale*s (natural-log domain)
+  float* l_state;    // FA_MODE_STATE: [bh, nq]
+  DebugChannel dbg;
+};
+
+template <int D>
+struct FaCfg {
+  static_assert(D == 64 || D == 128, "head dim must be 64 or 128");
+  static constexpr int kQT = 128;                       // query rows per tile
+  static constexpr int kKT = 128;                       // keys per tile
+  static constexpr int kBoxes = D / 64;                 // 64-column (128 B) TMA boxes per tile
+  static constexpr int kBoxBytes = 128 * 128;           // 128 rows x 128 B
+  static constexpr int kTileBytes = kBoxes * kBoxBytes; // one Q, K or V tile
+  static constexpr int kStages = (D == 128) ? 5 : 10;   // K/V ring depth
+  static constexpr int kThreads = 512;
+  static constexpr int kTmemCols = 512;
+  static constexpr uint32_t kColS0 = 0, kColS1 = 128, kColO0 = 256, kColO1 = 256 + D;
+  // smem carve-up (bytes from a 1024-aligned base)
+  static constexpr int kOffQ = 0;
+  static constexpr int kOffKV = 2 * kTileBytes;
+  static constexpr int kOffFac = kOffKV + kStages * kTileBytes;  // float[2][128] rescale factors / final m
+  static constexpr int kOffSum = kOffFac + 2 * 128 * 4;          // float[2][128] final l
+  static constexpr int kOffBar = kOffSum + 2 * 128 * 4;
+  static constexpr int kNumBars = 2 + 2 * kStages + 12;
+  static constexpr int kOffTmem = kOffBar + kNumBars * 8;
+  static constexpr int kSmemBytes = kOffTmem + 16;
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
+};
+
+// mbarrier wait sites (reported through the debug channel on a timeout)
+enum : uint32_t {
+  SITE_TMA_EMPTY = 1, SITE_MMA_QFULL, SITE_MMA_KVFULL, SITE_MMA_PFULL, SITE_MMA_CORR,
+  SITE_SM_SFULL, SITE_SM_CORR, SITE_CO_STATS, SITE_CO_LFULL, SITE_CO_OFULL
+};
+
+constexpr float kLazyRescaleTau = 8.0f;  // log2 units: P stays below 2^8, far inside fp16 range
+
+template <int D>
+__global__ void __launch_bounds__(512, 1)
+fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+              const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapO,
+              const FaParams p) {
+  using Cfg = FaCfg<D>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+
+  uint8_t* const q_smem = smem + Cfg::kOffQ;
+  uint8_t* const kv_smem = smem + Cfg::kOffKV;
+  float* const fac_smem = reinterpret_cast<float*>(smem + Cfg::kOffFac);
+  float* const sum_smem = reinterpret_cast<float*>(smem + Cfg::kOffSum);
+  uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBar);
+  uint64_t* const q_full = bars;                          // [2]
+  uint64_t* const kv_full = bars + 2;                     // [kStages]
+  uint64_t* const kv_empty = kv_full + Cfg::kStages;      // [kStages]
+  uint64_t* const s_full = kv_empty + Cfg::kStages;       // [2]  MMA -> softmax : S tile ready
+  uint64_t* const p_full = s_full + 2;                    // [2]  softmax -> MMA : P tile in TMEM
+  uint64_t* const stats_full = p_full + 2;                // [2]  softmax -> correction : factors
+  uint64_t* const corr_done = stats_full + 2;             // [2]  correction -> MMA : O rescaled
+  uint64_t* const o_full = corr_done + 2;                 // [2]  MMA -> correction : last PV done
+  uint64_t* const l_full = o_full + 2;                    // [2]  softmax -> correction : final l
+  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(smem + Cfg::kOffTmem);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int qblk = blockIdx.x % p.q_blocks;
+  const int bh = blockIdx.x / p.q_blocks;
+  const int q0 = qblk * 256;
+  const int ntile = (q0 + 128 < p.nq) ? 2 : 1;
+  const int nkv_tiles = (p.nkv + Cfg::kKT - 1) / Cfg::kKT;
+  const DebugChannel dbg = p.dbg;
+
+  // ------------------------------- one-time setup -------------------------------------
+  if (warp == 12 && lane == 0) {
+    if ((smem_u32(smem) & 1023u) != 0u) wait_timeout_trap(dbg, 0xA11u, 0, smem_u32(smem));
+    mbar_init(&q_full[0], 1);
+    mbar_init(&q_full[1], 1);
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 128);
+      mbar_init(&stats_full[i], 128);
+      mbar_init(&corr_done[i], 128);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&l_full[i], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 13 && lane == 0) {
+    prefetch_tensormap(&mapQ);
+    prefetch_tensormap(&mapK);
+    prefetch_tensormap(&mapV);
+    if (p.mode != FA_MODE_F32 && !(p.mode == FA_MODE_STATE && !p.is_last)) prefetch_tensormap(&mapO);
+  }
+  if (warp == 8) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 8) {
+    // =============================== softmax warpgroups ===============================
+    setmaxnreg_inc<192>();
+    const int i = warp >> 2;  // Q tile handled by this warpgroup
+    if (i < ntile) {
+      const int row = (warp & 3) * 32 + lane;
+      const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+      const uint32_t t_s = tmem_base + lane_base + (i == 0 ? Cfg::kColS0 : Cfg::kColS1);
+      float c = p.scale_log2;
+      const bool neg_scale = c < 0.f;  // max over scale*s == -|scale| * min(s): fold the sign into s
+      if (neg_scale) c = -c;
+      float m_used = -INFINITY;  // running max of (sign-folded) raw scores the exponent refers to
+      float l = 0.f;
+
+      for (int j = 0; j < nkv_tiles; ++j) {
+        mbar_wait(&s_full[i], j & 1, dbg, SITE_SM_SFULL, j);
+        tc_fence_after();
+        uint32_t sr[128];
+        tmem_ld_x32(t_s + 0, sr + 0);
+        tmem_ld_x32(t_s + 32, sr + 32);
+        tmem_ld_x32(t_s + 64, sr + 64);
+        tmem_ld_x32(t_s + 96, sr + 96);
+        tmem_wait_ld();
+        float* s = reinterpret_cast<float*>(sr);
+        if (neg_scale) {
+#pragma unroll
+          for (int k = 0; k < 128; ++k) s[k] = -s[k];
+        }
+        if (j == nkv_tiles - 1 && (p.nkv & 127) != 0) {
+          const int valid = p.nkv - j * 128;  // keys beyond nkv were zero-filled by TMA: mask them
+#pragma unroll
+          for (int k = 0; k < 128; ++k)
+            if (k >= valid) s[k] = -INFINITY;
+        }
+        // four independent 3-input max chains, one per 32-column quarter
+        float mx0 = s[0], mx1 = s[32], mx2 = s[64], mx3 = s[96];
+#pragma unroll
+        for (int k = 1; k < 31; k += 2) {
+          mx0 = fmax3(mx0, s[k], s[k + 1]);
+          mx1 = fmax3(mx1, s[32 + k], s[32 + k + 1]);
+          mx2 = fmax3(mx2, s[64 + k], s[64 + k + 1]);
+          mx3 = fmax3(mx3, s[96 + k], s[96 + k + 1]);
+        }
+        mx0 = fmax3(mx0, s[31], s[63]);
+        mx2 = fmax3(mx2, s[95], s[127]);
+        const float m_new = fmaxf(fmax3(mx0, mx1, mx2), fmaxf(mx3, m_used));
+
+        if (j == 0) {
+          m_used = m_new;
+        } else {
+          float fac = 1.f;
+          if ((m_new - m_used) * c > kLazyRescaleTau) {  // lazy: tolerate a stale max up to 2^tau
+            fac = ex2_approx((m_used - m_new) * c);
+            l *= fac;
+            m_used = m_new;
+          }
+          fac_smem[i * 128 + row] = fac;
+          mbar_arrive(&stats_full[i]);
+        }
+
+        const float neg_mc = -m_used * c;
+        float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int k = 0; k < 32; k += 4) {
+            const float p0 = ex2_approx(fmaf(s[q * 32 + k + 0], c, neg_mc));
+            const float p1 = ex2_approx(fmaf(s[q * 32 + k + 1], c, neg_mc));
+            const float p2 = ex2_approx(fmaf(s[q * 32 + k + 2], c, neg_mc));
+            const float p3 = ex2_approx(fmaf(s[q * 32 + k + 3], c, neg_mc));
+            l0 += p0; l1 += p1; l2 += p2; l3 += p3;
+            pk[k / 2 + 0] = pack_half2(p0, p1);
+            pk[k / 2 + 1] = pack_half2(p2, p3);
+          }
+          tmem_st_x16(t_s + q * 16, pk);  // P (fp16 pairs) overwrites columns [0,64) of its own S
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(&p_full[i]);
+        l += (l0 + l1) + (l2 + l3);
+      }
+
+      // final statistics for the epilogue
+      sum_smem[i * 128 + row] = l;
+      if (p.mode == FA_MODE_STATE) {
+        // fac_smem doubles as the final-max slot; the correction WG has consumed its last factor
+        // once corr_done completed its last phase.
+        if (nkv_tiles >= 2) mbar_wait(&corr_done[i], (nkv_tiles - 2) & 1, dbg, SITE_SM_CORR, i);
+        fac_smem[i * 128 + row] = neg_scale ? -m_used : m_used;  // raw-score max, true sign
+      }
+      mbar_arrive(&l_full[i]);
+    }
+  } else if (warp < 12) {
+    // ========================= correction + epilogue warpgroup ========================
+    setmaxnreg_dec<80>();
+    const int wq = warp & 3;
+    const int row = wq * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(wq * 32) << 16;
+
+    for (int j = 1; j < nkv_tiles; ++j) {
+      for (int i = 0; i < ntile; ++i) {
+        mbar_wait(&stats_full[i], (j - 1) & 1, dbg, SITE_CO_STATS, j);
+        const float fac = fac_smem[i * 128 + row];
+        if (__any_sync(0xffffffffu, fac != 1.f)) {
+          tc_fence_after();
+          const uint32_t t_o = tmem_base + lane_base + (i == 0 ? Cfg::kColO0 : Cfg::kColO1);
+#pragma unroll
+          for (int cc = 0; cc < D / 32; ++cc) {
+            uint32_t o[32];
+            tmem_ld_x32(t_o + cc * 32, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int k = 0; k < 32; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * fac);
+            tmem_st_x32(t_o + cc * 32, o);
+          }
+          tmem_wait_st();
+        }
+        tc_fence_before();
+        mbar_arrive(&corr_done[i]);
+      }
+    }
+
+    // ---- epilogue: O / l -> output ----
+    for (int i = 0; i < ntile; ++i) {
+      mbar_wait(&l_full[i], 0, dbg, SITE_CO_LFULL, i);
+      mbar_wait(&o_full[i], 0, dbg, SITE_CO_OFULL, i);
+      tc_fence_after();
+      const uint32_t t_o = tmem_base + lane_base + (i == 0 ? Cfg::kColO0 : Cfg::kColO1);
+      const int grow = q0 + i * 128 + row;  // query row inside this (b,h)
+      const bool row_ok = grow < p.nq;
+      float l_new = sum_smem[i * 128 + row];
+      float o_scale = 1.f;      // factor applied to this step's un-normalised O
+      float acc_scale = 0.f;    // factor applied to the carried O_acc (STATE mode)
+      bool emit_f16 = (p.mode == FA_MODE_F16);
+      bool emit_f32 = (p.mode == FA_MODE_F32);
+      bool emit_state = false;
+      const size_t row_index = static_cast<size_t>(bh) * p.nq + grow;
+      if (p.mode == FA_MODE_STATE) {
+        // Merge (O, m, l) of this K/V shard into the carried state: the reference's tile-to-tile
+        // rule, Streaming_FlashAttention_Forward_Kernel/flashattn_streaming_16x16.cu:247-261.
+        const float scale_ln = p.scale_log2 * 0.6931471805599453f;
+        const float m_new_s = fac_smem[i * 128 + row] * scale_ln;  // max of scale*s for this shard
+        float m_acc = -INFINITY, l_acc = 0.f;
+        if (!p.is_first && row_ok) {
+          m_acc = p.m_state[row_index];
+          l_acc = p.l_state[row_index];
+        }
+        const float m_tot = fmaxf(m_acc, m_new_s);
+        acc_scale = (m_acc == -INFINITY) ? 0.f : ex2_approx((m_acc - m_tot) * 1.4426950408889634f);
+        o_scale = ex2_approx((m_new_s - m_tot) * 1.4426950408889634f);
+        const float l_tot = l_acc * acc_scale + l_new * o_scale;
+        if (p.is_last) {
+          emit_f16 = true;
+          const float inv = 1.f / l_tot;
+          o_scale *= inv;
+          acc_scale *= inv;
+        } else {
+          emit_state = true;
+          if (row_ok) {
+            p.m_state[row_index] = m_tot;
+            p.l_state[row_index] = l_tot;
+          }
+        }
+      } else {
+        o_scale = 1.f / l_new;
+      }
+      const bool have_acc = (p.mode == FA_MODE_STATE) && !p.is_first;
+      float* const acc_row = p.o_f32 + row_index * D;
+      uint8_t* const stage = q_smem + i * Cfg::kTileBytes;  // Q tile i is dead once o_full fired
+
+#pragma unroll
+      for (int cc = 0; cc < D / 32; ++cc) {
+        uint32_t o[32];
+        tmem_ld_x32(t_o + cc * 32, o);
+        tmem_wait_ld();
+        float v[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(o[k]) * o_scale;
+        if (have_acc && row_ok) {
+#pragma unroll
+          for (int k = 0; k < 32; k += 4) {
+            const float4 a = *reinterpret_cast<const float4*>(acc_row + cc * 32 + k);
+            v[k + 0] = fmaf(a.x, acc_scale, v[k + 0]);
+            v[k + 1] = fmaf(a.y, acc_scale, v[k + 1]);
+            v[k + 2] = fmaf(a.z, acc_scale, v[k + 2]);
+            v[k + 3] = fmaf(a.w, acc_scale, v[k + 3]);
+          }
+        }
+        if (emit_f16) {
+          // 32 columns = 64 B = four 16-byte chunks of this row inside a 128B-swizzled box
+          uint8_t* const box = stage + (cc >> 1) * Cfg::kBoxBytes + row * 128;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 w;
+            w.x = pack_half2(v[q * 8 + 0], v[q * 8 + 1]);
+            w.y = pack_half2(v[q * 8 + 2], v[q * 8 + 3]);
+            w.z = pack_half2(v[q * 8 + 4], v[q * 8 + 5]);
+            w.w = pack_half2(v[q * 8 + 6], v[q * 8 + 7]);
+            const int chunk = (cc & 1) * 4 + q;
+            *reinterpret_cast<uint4*>(box + ((chunk ^ (row & 7)) << 4)) = w;
+          }
+        } else if ((emit_f32 || emit_state) && row_ok) {
+#pragma unroll
+          for (int k = 0; k < 32; k += 4)
+            *reinterpret_cast<float4*>(acc_row + cc * 32 + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+        }
+      }
+      if (emit_f16) {
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (warp == 8 && lane == 0) {
+#pragma unroll
+          for (int b = 0; b < Cfg::kBoxes; ++b)
+            tma_store_3d(&mapO, stage + b * Cfg::kBoxBytes, b * 64, q0 + i * 128, bh);  // clips rows >= nq
+          tma_store_commit();
+        }
+      }
+    }
+    if (warp == 8 && lane == 0) tma_store_wait_all<0>();
+  } else if (warp == 12) {
+    // ================================ MMA issuer ======================================
+    setmaxnreg_dec<48>();
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = umma_idesc_f16(128, 128, 0, 0);
+      constexpr uint32_t idesc_pv = umma_idesc_f16(128, D, 0, 1);
+      const uint32_t q_addr = smem_u32(q_smem);
+      const uint32_t kv_addr = smem_u32(kv_smem);
+
+      auto issue_qk = [&](int i, int slot) {
+        const uint32_t a0 = q_addr + i * Cfg::kTileBytes;
+        const uint32_t b0 = kv_addr + slot * Cfg::kTileBytes;
+        const uint32_t d = tmem_base + (i == 0 ? Cfg::kColS0 : Cfg::kColS1);
+#pragma unroll
+        for (int ks = 0; ks < D / 16; ++ks) {
+          const uint32_t off = (ks >> 2) * Cfg::kBoxBytes + (ks & 3) * 32;
+          umma_ss(d, umma_desc_sw128(a0 + off, 16, 1024), umma_desc_sw128(b0 + off, 16, 1024), idesc_qk,
+                  ks > 0 ? 1u : 0u);
+        }
+      };
+      auto issue_pv = [&](int i, int slot, bool accumulate) {
+        const uint32_t b0 = kv_addr + slot * Cfg::kTileBytes;
+        const uint32_t d = tmem_base + (i == 0 ? Cfg::kColO0 : Cfg::kColO1);
+        const uint32_t a = tmem_base + (i == 0 ? Cfg::kColS0 : Cfg::kColS1);
+#pragma unroll
+        for (int ks = 0; ks < Cfg::kKT / 16; ++ks) {
+          // V tile: rows = keys (128 B of head dim each): MN-major B operand, 16 keys = 2048 B per step
+          umma_ts(d, a + ks * 8, umma_desc_sw128(b0 + ks * 2048, Cfg::kBoxBytes, 1024), idesc_pv,
+                  (accumulate || ks > 0) ? 1u : 0u);
+        }
+      };
+      auto slot_of = [](int t) { return t % Cfg::kStages; };
+      auto par_of = [](int t) { return (t / Cfg::kStages) & 1; };
+
+      // prologue: S_i(0) = Q_i K(0)^T
+      mbar_wait(&q_full[0], 0, dbg, SITE_MMA_QFULL, 0);
+      mbar_wait(&kv_full[slot_of(0)], par_of(0), dbg, SITE_MMA_KVFULL, 0);
+      tc_fence_after();
+      issue_qk(0, slot_of(0));
+      umma_commit(&s_full[0]);
+      if (ntile == 2) {
+        mbar_wait(&q_full[1], 0, dbg, SITE_MMA_QFULL, 1);
+        tc_fence_after();
+        issue_qk(1, slot_of(0));
+        umma_commit(&s_full[1]);
+      }
+      umma_commit(&kv_empty[slot_of(0)]);
+
+      for (int j = 0; j < nkv_tiles; ++j) {
+        const int tv = 2 * j + 1, tk = 2 * j + 2;
+        const bool more = (j + 1 < nkv_tiles);
+        mbar_wait(&kv_full[slot_of(tv)], par_of(tv), dbg, SITE_MMA_KVFULL, tv);
+        for (int i = 0; i < ntile; ++i) {
+          mbar_wait(&p_full[i], j & 1, dbg, SITE_MMA_PFULL, j);
+          if (j > 0) mbar_wait(&corr_done[i], (j - 1) & 1, dbg, SITE_MMA_CORR, j);
+          tc_fence_after();
+          issue_pv(i, slot_of(tv), j > 0);
+          if (!more) umma_commit(&o_full[i]);
+          if (more) {
+            if (i == 0) {
+              mbar_wait(&kv_full[slot_of(tk)], par_of(tk), dbg, SITE_MMA_KVFULL, tk);
+              tc_fence_after();
+            }
+            issue_qk(i, slot_of(tk));
+            umma_commit(&s_full[i]);
+          }
+        }
+        umma_commit(&kv_empty[slot_of(tv)]);
+        if (more) umma_commit(&kv_empty[slot_of(tk)]);
+      }
+    }
+  } else if (warp == 13) {
+    // ================================ TMA producer ====================================
+    setmaxnreg_dec<48>();
+    if (lane == 0) {
+      auto load_tile = [&](const CUtensorMap* map, uint8_t* dst, uint64_t* bar, int row0, uint64_t hint) {
+        mbar_arrive_expect_tx(bar, Cfg::kTileBytes);
+#pragma unroll
+        for (int b = 0; b < Cfg::kBoxes; ++b) tma_load_3d(dst + b * Cfg::kBoxBytes, map, bar, b * 64, row0, bh, hint);
+      };
+      load_tile(&mapQ, q_smem, &q_full[0], q0, kEvictFirst);
+      const int total = 2 * nkv_tiles;
+      for (int t = 0; t < total; ++t) {
+        const int slot = t % Cfg::kStages;
+        const int par = (t / Cfg::kStages) & 1;
+        mbar_wait(&kv_empty[slot], par ^ 1, dbg, SITE_TMA_EMPTY, t);
+        load_tile((t & 1) ? &mapV : &mapK, kv_smem + slot * Cfg::kTileBytes, &kv_full[slot], (t >> 1) * Cfg::kKT,
+                  kEvictLast);
+        if (t == 0 && ntile == 2) load_tile(&mapQ, q_smem + Cfg::kTileBytes, &q_full[1], q0 + 128, kEvictFirst);
+      }
+    }
+  } else {
+    setmaxnreg_dec<48>();
+  }
+
+  // ---------------------------------- teardown ----------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 8) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+}  // namespace fa

@@ -1,0 +1,184 @@
+"""Host-side mirror of the reference's operator surface, one function per C-ABI entry point.
+
+Tensors are torch CUDA tensors (torch is plumbing here: device memory and streams); the *_host
+variants take numpy arrays / pinned torch CPU tensors and run the reference's main() flow
+(H2D -> kernel -> D2H) inside the library.  Argument meaning follows the reference kernels:
+flat (B*H) batches of row-major [N, D] matrices, explicit `scale`, epilogue order
+bias -> ReLU -> residual with nullable bias / residual.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from ._lib import check, load_library
+
+
+def _stream_ptr(stream=None):
+    s = torch.cuda.current_stream() if stream is None else stream
+    return ctypes.c_void_p(s.cuda_stream)
+
+
+def _dev_ptr(t, dtype, name):
+    if t is None:
+        return None
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError(f"{name} must be a CUDA tensor (no CPU fallback exists)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous (row-major)")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _bhnd(q):
+    if q.dim() != 4:
+        raise ValueError("expected a [B, H, N, D] tensor")
+    return tuple(int(x) for x in q.shape)
+
+
+def fa_forward(q, k, v, scale=None, out=None, stream=None):
+    """O = softmax(scale * Q K^T) V, fp16 [B,H,N,D] in and out (include/fa_b200.h: fa_forward)."""
+    B, H, N, D = _bhnd(q)
+    if tuple(k.shape) != (B, H, N, D) or tuple(v.shape) != (B, H, N, D):
+        raise ValueError("Q, K, V must share the shape [B, H, N, D]")
+    if scale is None:
+        scale = 1.0 / float(D) ** 0.5  # the reference's default (v12i.cu:307)
+    if out is None:
+        out = torch.empty_like(q)
+    lib = load_library()
+    with torch.cuda.device(q.device):
+        check(lib.fa_forward(_dev_ptr(q, torch.float16, "Q"), _dev_ptr(k, torch.float16, "K"),
+                             _dev_ptr(v, torch.float16, "V"), _dev_ptr(out, torch.float16, "O"),
+                             B, H, N, D, float(scale), _stream_ptr(stream)), "fa_forward")
+    return out
+
+
+def fa_forward_f32out(q, k, v, scale=None, out=None, stream=None):
+    """Same with the reference kernels' fp32 output (flashattn_forward_wmma.cu:49-58)."""
+    B, H, N, D = _bhnd(q)
+    if tuple(k.shape) != (B, H, N, D) or tuple(v.shape) != (B, H, N, D):
+        raise ValueError("Q, K, V must share the shape [B, H, N, D]")
+    if scale is None:
+        scale = 1.0 / float(D) ** 0.5
+    if out is None:
+        out = torch.empty((B, H, N, D), dtype=torch.float32, device=q.device)
+    lib = load_library()
+    with torch.cuda.device(q.device):
+        check(lib.fa_forward_f32out(_dev_ptr(q, torch.float16, "Q"), _dev_ptr(k, torch.float16, "K"),
+                                    _dev_ptr(v, torch.float16, "V"), _dev_ptr(out, torch.float32, "O"),
+                                    B, H, N, D, float(scale), _stream_ptr(stream)), "fa_forward_f32out")
+    return out
+
+
+def fa_forward_partial(q, k, v, o_acc, m, l, scale, is_first, is_last, o_final=None, stream=None):
+    """One ring step: fold attention of Q against one K/V shard into the carried (O_acc, m, l)."""
+    B, H, Nq, D = _bhnd(q)
+    Bk, Hk, Nkv, Dk = _bhnd(k)
+    if (Bk, Hk, Dk) != (B, H, D) or tuple(v.shape) != tuple(k.shape):
+        raise ValueError("K, V must be [B, H, Nkv, D] matching Q's B, H, D")
+    if is_last and o_final is None:
+        o_final = torch.empty_like(q)
+    lib = load_library()
+    with torch.cuda.device(q.device):
+        check(lib.fa_forward_partial(_dev_ptr(q, torch.float16, "Q"), _dev_ptr(k, torch.float16, "K"),
+                                     _dev_ptr(v, torch.float16, "V"), _dev_ptr(o_acc, torch.float32, "O_acc"),
+                                     _dev_ptr(m, torch.float32, "m"), _dev_ptr(l, torch.float32, "l"),
+                                     B, H, Nq, Nkv, D, float(scale), int(bool(is_first)), int(bool(is_last)),
+                                     _dev_ptr(o_final, torch.float16, "O_final") if is_last else None,
+                                     _stream_ptr(stream)), "fa_forward_partial")
+    return o_final
+
+
+def gemm_fused_epilogue(a, b, bias=None, residual=None, out=None, stream=None):
+    """C = ReLU(A @ B + bias) + residual; A fp16 [M,K], B fp16 [K,N], fp32 bias/residual/C."""
+    if a.dim() != 2 or b.dim() != 2 or a.shape[1] != b.shape[0]:
+        raise ValueError("A must be [M, K] and B [K, N]")
+    M, K = int(a.shape[0]), int(a.shape[1])
+    N = int(b.shape[1])
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    if bias is not None and tuple(bias.shape) != (N,):
+        raise ValueError("bias must be [N]")
+    if residual is not None and tuple(residual.shape) != (M, N):
+        raise ValueError("residual must be [M, N]")
+    lib = load_library()
+    with torch.cuda.device(a.device):
+        check(lib.gemm_fused_epilogue(_dev_ptr(a, torch.float16, "A"), _dev_ptr(b, torch.float16, "B"),
+                                      _dev_ptr(bias, torch.float32, "bias"),
+                                      _dev_ptr(residual, torch.float32, "residual"),
+                                      _dev_ptr(out, torch.float32, "C"), M, N, K, _stream_ptr(stream)),
+              "gemm_fused_epilogue")
+    return out
+
+
+def softmax_rows(x, out=None, stream=None):
+    """Row softmax of an fp32 [rows, N] matrix (softmax_naive_baseline.cu:56-61)."""
+    if x.dim() != 2:
+        raise ValueError("expected a [rows, N] tensor")
+    rows, N = int(x.shape[0]), int(x.shape[1])
+    if out is None:
+        out = torch.empty_like(x)
+    lib = load_library()
+    with torch.cuda.device(x.device):
+        check(lib.softmax_rows(_dev_ptr(x, torch.float32, "X"), _dev_ptr(out, torch.float32, "P"), rows, N,
+                               _stream_ptr(stream)), "softmax_rows")
+    return out
+
+
+# ----------------------------- host-buffer variants ------------------------------------
+def _host_ptr(a, dtype, name):
+    if a is None:
+        return None
+    if isinstance(a, torch.Tensor):
+        if a.is_cuda:
+            raise TypeError(f"{name}: the *_host entry points take host memory")
+        if not a.is_contiguous():
+            raise ValueError(f"{name} must be contiguous")
+        return ctypes.c_void_p(a.data_ptr())
+    if not isinstance(a, np.ndarray) or a.dtype != dtype or not a.flags["C_CONTIGUOUS"]:
+        raise TypeError(f"{name} must be a C-contiguous numpy array of {dtype}")
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+def fa_forward_host(q, k, v, out, scale=None):
+    """fa_forward on HOST buffers (fp16 [B,H,N,D]); copies are part of the call."""
+    B, H, N, D = (int(x) for x in q.shape)
+    if scale is None:
+        scale = 1.0 / float(D) ** 0.5
+    lib = load_library()
+    check(lib.fa_forward_host(_host_ptr(q, np.float16, "Q"), _host_ptr(k, np.float16, "K"),
+                              _host_ptr(v, np.float16, "V"), _host_ptr(out, np.float16, "O"),
+                              B, H, N, D, float(scale)), "fa_forward_host")
+    return out
+
+
+def gemm_fused_epilogue_host(a, b, bias, residual, out):
+    M, K = (int(x) for x in a.shape)
+    N = int(b.shape[1])
+    lib = load_library()
+    check(lib.gemm_fused_epilogue_host(_host_ptr(a, np.float16, "A"), _host_ptr(b, np.float16, "B"),
+                                       _host_ptr(bias, np.float32, "bias"), _host_ptr(residual, np.float32, "residual"),
+                                       _host_ptr(out, np.float32, "C"), M, N, K), "gemm_fused_epilogue_host")
+    return out
+
+
+def softmax_rows_host(x, out):
+    rows, N = (int(v) for v in x.shape)
+    lib = load_library()
+    check(lib.softmax_rows_host(_host_ptr(x, np.float32, "X"), _host_ptr(out, np.float32, "P"), rows, N),
+          "softmax_rows_host")
+    return out
+
+
+def launch_count():
+    """Kernels launched by the library in this process."""
+    return int(load_library().fa_launch_count())
+
+
+def last_debug():
+    """The hang-diagnostic record (list of ints), empty if none was written."""
+    buf = (ctypes.c_uint * 8)()
+    n = load_library().fa_last_debug(buf, 8)
+    words = [int(buf[i]) for i in range(n)]
+    return words if words and words[0] == 0xDEAD0001 else []

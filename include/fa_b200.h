@@ -1,0 +1,123 @@
+/*
+ * fa_b200.h -- C ABI of the B200-native (sm_100a) FlashAttention-forward engine.
+ *
+ * Drop-in boundary for the hot path of jeehun98/FlashAttention_Kernel_Project. The reference
+ * has no library target: its operator surface is the parameter lists of its __global__ kernels
+ * plus the main() conventions around them. Each entry point below names the reference interface
+ * it replaces (paths relative to the reference repo).
+ *
+ * Conventions shared by every entry point
+ *   - all tensor pointers are DEVICE pointers owned by the caller (the *_host variants take HOST
+ *     pointers and perform the copies the reference's main() performs); nothing is retained;
+ *   - row-major, contiguous; fp16 tensors are IEEE binary16 (`__half`), passed as `const void*`
+ *     so this header needs no CUDA headers;
+ *   - `stream` is a `cudaStream_t` (NULL = default stream); work is enqueued asynchronously;
+ *   - return value: 0 on success, a negative FA_ERR_* for a rejected call, a positive
+ *     `cudaError_t` for a CUDA runtime failure.  Nothing is printed and the process is never
+ *     aborted (the reference's CHECK_CUDA macro exits; its kernels silently `return` on
+ *     unsupported shapes, e.g. FlashAttention/flashattn_forward_wmma/flashattn_forward_wmma.cu:63);
+ *   - there is NO CPU fallback: without an sm_100 device every compute call returns
+ *     FA_ERR_NO_DEVICE.
+ */
+#ifndef FA_B200_H_
+#define FA_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FA_OK 0
+#define FA_ERR_BAD_SHAPE (-1)      /* non-positive extent, or product overflows the index range   */
+#define FA_ERR_BAD_HEAD_DIM (-2)   /* D not in {64, 128}                                          */
+#define FA_ERR_MISALIGNED (-3)     /* pointer not 16-byte aligned / row pitch not a multiple of 16 B */
+#define FA_ERR_NULL_POINTER (-4)
+#define FA_ERR_NO_DEVICE (-5)      /* current device is not compute capability 10.x               */
+#define FA_ERR_DRIVER_ENTRY (-6)   /* cuTensorMapEncodeTiled could not be resolved / failed       */
+#define FA_ERR_BAD_ARGUMENT (-7)
+
+/* Library version: major*10000 + minor*100 + patch. */
+int fa_version(void);
+/* Static string for a return code of this library (negative) or of CUDA (positive). */
+const char* fa_strerror(int code);
+
+/*
+ * Non-causal attention forward, O = softmax(scale * Q K^T) V, per (b, h).
+ *   Q, K, V : fp16 [B, H, N, D];  O : fp16 [B, H, N, D];  D in {64, 128};  any N >= 1.
+ * Replaces: flashattn_forward_wmma_v5_cp_async_kernel(Q, K, V, O, BH, N, D, scale)
+ *   (FlashAttention/flashattn_forward_memory_bound/flashattn_forward_wmma_v5_cp_async.cu:99-108)
+ * and flashattn_forward_wmma_v4_kernel (FlashAttention/flashattn_forward_wmma/flashattn_forward_wmma_v4.cu:52-61);
+ * the same math as the named comparators flashattn_2warp_nosmemW_online_softmax
+ *   (flashattn_warp_spc/flashattn_streaming_16x32_2warp_softmax_v12i.cu:60-70).
+ * B*H is the reference's flat `BH` batch; `scale` is explicit as in the reference (1/sqrt(D) there).
+ */
+int fa_forward(const void* Q, const void* K, const void* V, void* O, int B, int H, int N, int D,
+               float scale, void* stream);
+
+/* Same, fp32 output as the reference kernels write it (`float* O`, flashattn_forward_wmma.cu:49-58). */
+int fa_forward_f32out(const void* Q, const void* K, const void* V, float* O, int B, int H, int N, int D,
+                      float scale, void* stream);
+
+/*
+ * One step of a context-parallel (ring) attention: attends Q [B,H,Nq,D] to ONE K/V shard
+ * [B,H,Nkv,D] and folds the result into the carried state
+ *   O_acc fp32 [B,H,Nq,D] (un-normalised), m fp32 [B,H,Nq] (running row max of scale*QK^T),
+ *   l fp32 [B,H,Nq] (running row sum),
+ * with the merge rule the reference applies tile to tile
+ *   (Streaming_FlashAttention_Forward_Kernel/flashattn_streaming_16x16.cu:247-261).
+ * is_first != 0: the incoming state is ignored (treated as empty).
+ * is_last  != 0: additionally writes the normalised result to O_final (fp16 [B,H,Nq,D]);
+ *                O_final may be NULL otherwise.
+ * The reference has no multi-GPU path; this entry exists for BASELINE config 4.
+ */
+int fa_forward_partial(const void* Q, const void* K, const void* V, float* O_acc, float* m, float* l,
+                       int B, int H, int Nq, int Nkv, int D, float scale, int is_first, int is_last,
+                       void* O_final, void* stream);
+
+/*
+ * C = ReLU(A*B + bias[col]) + residual   (epilogue order: bias -> ReLU -> residual).
+ *   A fp16 [M,K] row-major; Bm fp16 [K,N] row-major (NOT transposed); bias fp32 [N] or NULL;
+ *   residual fp32 [M,N] or NULL; C fp32 [M,N].  K % 8 == 0 and N % 8 == 0 (16-byte row pitch).
+ * Replaces: wmma_gemm_fused_kernel(A, B, bias, residual, C, M, N, K)
+ *   (GEMM/tensorcore_gemm_fused_epilogue/tensorcore_gemm_fused_epilogue.cu:53-58, epilogue :109-126).
+ */
+int gemm_fused_epilogue(const void* A, const void* Bm, const float* bias, const float* residual, float* C,
+                        int M, int N, int K, void* stream);
+
+/*
+ * Row softmax, P[r, :] = softmax(X[r, :]) with max subtraction; X, P fp32 [rows, N]; in place allowed.
+ * Replaces: softmax_naive_baseline_kernel(scores, probs, num_rows, N)
+ *   (Softmax micro kernel/softmax_naive_baseline/softmax_naive_baseline.cu:56-61).
+ */
+int softmax_rows(const float* X, float* P, int rows, int N, void* stream);
+
+/*
+ * Host-buffer variants: the flow of the reference's main() (cudaMalloc -> H2D -> launch -> D2H,
+ * e.g. flashattn_streaming_16x32_2warp_softmax_v12i.cu:325-368) behind one call.  All pointers
+ * are HOST pointers (pinned memory makes the copies asynchronous); device scratch is cached
+ * inside the library per device and grown on demand.  The call returns after the result is in
+ * the host buffer.  fa_host_release() frees the cached scratch of the current device.
+ */
+int fa_forward_host(const void* Q, const void* K, const void* V, void* O, int B, int H, int N, int D,
+                    float scale);
+int gemm_fused_epilogue_host(const void* A, const void* Bm, const float* bias, const float* residual,
+                             float* C, int M, int N, int K);
+int softmax_rows_host(const float* X, float* P, int rows, int N);
+int fa_host_release(void);
+
+/*
+ * Hang diagnostics: every mbarrier wait in the kernels is bounded (2 s); on expiry the kernel
+ * records where it was stuck and traps.  fa_last_debug copies up to `n` 32-bit words of that
+ * record (word0 = 0xDEAD0001 if a record exists; site, blockIdx.x, blockIdx.y, threadIdx.x,
+ * parity, tag follow) and returns the number of words written.  The B200-native counterpart of
+ * the reference's "[STUCK]" printf hang hunt
+ * (flashattn_warp_spc_v2/flashattn_streaming_16x16_mw_v7_2_dbg_hanghunt.cu:163,231-233).
+ */
+int fa_last_debug(unsigned int* words, int n);
+
+/* Number of kernels this library has launched in this process (all entry points). */
+unsigned long long fa_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FA_B200_H_ */
