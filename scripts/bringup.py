@@ -1,8 +1,11 @@
 """GPU bring-up checks (developer tool, not part of the pytest suite): each case runs in its own
 process so a trapped kernel cannot poison the others.  Usage: python scripts/bringup.py [case ...]"""
+import os
 import subprocess
 import sys
 import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import torch
 
