@@ -32,9 +32,16 @@ def _dev_ptr(t, dtype, name):
 
 
 def _bhnd(q):
+    if not isinstance(q, torch.Tensor) or not q.is_cuda:
+        raise TypeError("expected a CUDA tensor (no CPU fallback exists)")
     if q.dim() != 4:
         raise ValueError("expected a [B, H, N, D] tensor")
     return tuple(int(x) for x in q.shape)
+
+
+def _require_cuda(t, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError(f"{name} must be a CUDA tensor (no CPU fallback exists)")
 
 
 def fa_forward(q, k, v, scale=None, out=None, stream=None):
@@ -92,6 +99,8 @@ def fa_forward_partial(q, k, v, o_acc, m, l, scale, is_first, is_last, o_final=N
 
 def gemm_fused_epilogue(a, b, bias=None, residual=None, out=None, stream=None):
     """C = ReLU(A @ B + bias) + residual; A fp16 [M,K], B fp16 [K,N], fp32 bias/residual/C."""
+    _require_cuda(a, "A")
+    _require_cuda(b, "B")
     if a.dim() != 2 or b.dim() != 2 or a.shape[1] != b.shape[0]:
         raise ValueError("A must be [M, K] and B [K, N]")
     M, K = int(a.shape[0]), int(a.shape[1])
@@ -114,6 +123,7 @@ def gemm_fused_epilogue(a, b, bias=None, residual=None, out=None, stream=None):
 
 def softmax_rows(x, out=None, stream=None):
     """Row softmax of an fp32 [rows, N] matrix (softmax_naive_baseline.cu:56-61)."""
+    _require_cuda(x, "X")
     if x.dim() != 2:
         raise ValueError("expected a [rows, N] tensor")
     rows, N = int(x.shape[0]), int(x.shape[1])

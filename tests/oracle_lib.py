@@ -1,0 +1,263 @@
+"""ctypes access to the CHECKER: oracle/libfa_oracle.so (C restatement of the reference's host
+oracles) and, when present, oracle/_ref/libref_*.so (the reference's own functions and kernels,
+compiled unmodified).  Test infrastructure only -- nothing under flashattention_kernel_project_b200/
+imports this."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+REF_DIR = os.path.join(ORACLE_DIR, "_ref")
+
+_f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+_u16p = np.ctypeslib.ndpointer(dtype=np.uint16, flags="C_CONTIGUOUS")
+_i64p = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
+c_int, c_float, c_size_t, c_double, c_ll = ctypes.c_int, ctypes.c_float, ctypes.c_size_t, ctypes.c_double, ctypes.c_longlong
+
+
+def _as_u16(a):
+    a = np.ascontiguousarray(a)
+    if a.dtype == np.float16:
+        return a.view(np.uint16)
+    assert a.dtype == np.uint16
+    return a
+
+
+def _opt_f32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float32).ctypes.data_as(ctypes.c_void_p)
+
+
+class Oracle:
+    """The C restatement (oracle/fa_oracle.c)."""
+
+    def __init__(self):
+        path = os.path.join(ORACLE_DIR, "libfa_oracle.so")
+        if not os.path.exists(path):
+            subprocess.run(["make", "-s", "-C", ORACLE_DIR, "oracle"], check=True)
+        L = ctypes.CDLL(path)
+        L.fa_oracle_attention_f16.argtypes = [_u16p, _u16p, _u16p, _f32p] + [c_int] * 5 + [c_float, c_int]
+        L.fa_oracle_attention_f16_rows.argtypes = [_u16p, _u16p, _u16p, _f32p, _i64p] + [c_int] * 6 + [c_float, c_int]
+        L.fa_oracle_attention_f32_dacc.argtypes = [_f32p] * 4 + [c_int] * 3
+        L.fa_oracle_attention_f32.argtypes = [_f32p] * 4 + [c_int] * 3 + [c_float]
+        L.fa_oracle_softmax_rows.argtypes = [_f32p, _f32p, c_ll, c_int, c_int]
+        L.fa_oracle_gemm_fused.argtypes = [_f32p, _f32p, ctypes.c_void_p, ctypes.c_void_p, _f32p] + [c_int] * 6
+        L.fa_oracle_gemm_fused_f16.argtypes = [_u16p, _u16p, ctypes.c_void_p, ctypes.c_void_p, _f32p] + [c_int] * 6
+        L.fa_oracle_rel_l2.argtypes = [_f32p, _f32p, c_size_t]
+        L.fa_oracle_rel_l2.restype = c_double
+        L.fa_oracle_max_abs.argtypes = [_f32p, _f32p, c_size_t]
+        L.fa_oracle_max_abs.restype = c_double
+        L.fa_oracle_half_to_float.argtypes = [_u16p, _f32p, c_size_t]
+        L.fa_oracle_float_to_half.argtypes = [_f32p, _u16p, c_size_t]
+        L.fa_oracle_num_threads.restype = c_int
+        self.L = L
+
+    def num_threads(self):
+        return int(self.L.fa_oracle_num_threads())
+
+    def attention_f16(self, q, k, v, scale, nthreads=0):
+        """q [B, M, KDIM], k [B, L, KDIM], v [B, L, DV] fp16 -> fp32 [B, M, DV] (v12i cpu_reference)."""
+        B, M, KD = q.shape
+        Lk, DV = k.shape[1], v.shape[2]
+        out = np.empty((B, M, DV), dtype=np.float32)
+        self.L.fa_oracle_attention_f16(_as_u16(q), _as_u16(k), _as_u16(v), out, B, M, Lk, KD, DV, float(scale), nthreads)
+        return out
+
+    def attention_f16_rows(self, q, k, v, scale, rows, nthreads=0):
+        """Sampled rows (flat ids b*M + m) -> fp32 [len(rows), DV]."""
+        B, M, KD = q.shape
+        Lk, DV = k.shape[1], v.shape[2]
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        out = np.empty((len(rows), DV), dtype=np.float32)
+        self.L.fa_oracle_attention_f16_rows(_as_u16(q), _as_u16(k), _as_u16(v), out, rows, len(rows), B, M, Lk, KD, DV,
+                                            float(scale), nthreads)
+        return out
+
+    def attention_f32_dacc(self, q, k, v):
+        BH, N, D = q.shape
+        out = np.empty((BH, N, D), dtype=np.float32)
+        self.L.fa_oracle_attention_f32_dacc(*(np.ascontiguousarray(x, dtype=np.float32) for x in (q, k, v)), out, BH, N, D)
+        return out
+
+    def attention_f32(self, q, k, v, scale):
+        BH, N, D = q.shape
+        out = np.empty((BH, N, D), dtype=np.float32)
+        self.L.fa_oracle_attention_f32(*(np.ascontiguousarray(x, dtype=np.float32) for x in (q, k, v)), out, N, D, BH,
+                                       float(scale))
+        return out
+
+    def softmax_rows(self, x, nthreads=0):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        out = np.empty_like(x)
+        self.L.fa_oracle_softmax_rows(x, out, x.shape[0], x.shape[1], nthreads)
+        return out
+
+    def gemm_fused(self, a, b, bias, residual, row_begin=0, row_end=None, nthreads=0):
+        """fp32 operands, full [M, N] result buffer; only rows [row_begin, row_end) are computed."""
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        b = np.ascontiguousarray(b, dtype=np.float32)
+        M, K = a.shape
+        N = b.shape[1]
+        row_end = M if row_end is None else row_end
+        out = np.zeros((M, N), dtype=np.float32)
+        self.L.fa_oracle_gemm_fused(a, b, _opt_f32(bias), _opt_f32(residual), out, M, N, K, row_begin, row_end, nthreads)
+        return out
+
+    def gemm_fused_f16(self, a, b, bias, residual, row_begin=0, row_end=None, nthreads=0):
+        """fp16 operands (widened to fp32, as the GPU is fed); returns rows [row_begin, row_end)."""
+        M, K = a.shape
+        N = b.shape[1]
+        row_end = M if row_end is None else row_end
+        out = np.empty((row_end - row_begin, N), dtype=np.float32)
+        self.L.fa_oracle_gemm_fused_f16(_as_u16(a), _as_u16(b), _opt_f32(bias), _opt_f32(residual), out, M, N, K,
+                                        row_begin, row_end, nthreads)
+        return out
+
+    def rel_l2(self, a, b):
+        a = np.ascontiguousarray(a, dtype=np.float32).ravel()
+        b = np.ascontiguousarray(b, dtype=np.float32).ravel()
+        return float(self.L.fa_oracle_rel_l2(a, b, a.size))
+
+    def max_abs(self, a, b):
+        a = np.ascontiguousarray(a, dtype=np.float32).ravel()
+        b = np.ascontiguousarray(b, dtype=np.float32).ravel()
+        return float(self.L.fa_oracle_max_abs(a, b, a.size))
+
+    def half_to_float(self, h):
+        h = _as_u16(h).ravel()
+        out = np.empty(h.size, dtype=np.float32)
+        self.L.fa_oracle_half_to_float(h, out, h.size)
+        return out
+
+    def float_to_half(self, f):
+        f = np.ascontiguousarray(f, dtype=np.float32).ravel()
+        out = np.empty(f.size, dtype=np.uint16)
+        self.L.fa_oracle_float_to_half(f, out, f.size)
+        return out
+
+
+def ref_available(name):
+    return os.path.exists(os.path.join(REF_DIR, f"libref_{name}.so"))
+
+
+class RefLib:
+    """The reference's own code (oracle/_ref/libref_<name>.so), one library per reference file."""
+
+    def __init__(self, name):
+        path = os.path.join(REF_DIR, f"libref_{name}.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.L = ctypes.CDLL(path, mode=ctypes.RTLD_LOCAL)
+        self.name = name
+
+
+class RefCpu:
+    """Host-side functions of the reference (no GPU needed)."""
+
+    def __init__(self):
+        self.v12i = RefLib("v12i").L
+        self.v12i.ref_v12i_cpu_reference.argtypes = [_u16p, _u16p, _u16p, _f32p] + [c_int] * 5 + [c_float]
+        self.v12i.ref_v12i_rel_l2.argtypes = [_f32p, _f32p, c_size_t]
+        self.v12i.ref_v12i_rel_l2.restype = c_double
+        self.v12i.ref_v12i_fill_uniform.argtypes = [ctypes.c_uint, _u16p, c_size_t, _u16p, c_size_t, _u16p, c_size_t]
+        self.fa542 = RefLib("fa542").L
+        self.fa542.ref_fa542_cpu_ref.argtypes = [_f32p] * 4 + [c_int] * 3
+        self.sb = RefLib("softmax_block").L
+        self.sb.ref_softmax_block_flashattn_ref.argtypes = [_f32p] * 4 + [c_int] * 3 + [c_float]
+        self.gemm = RefLib("gemm_fused").L
+        self.gemm.ref_gemm_fused_cpu.argtypes = [_f32p] * 5 + [c_int] * 3
+        self.gemm.ref_gemm_fused_fill.argtypes = [ctypes.c_uint] + [_f32p, c_size_t] * 4
+
+    def v12i_cpu_reference(self, q, k, v, scale):
+        B, M, KD = q.shape
+        Lk, DV = k.shape[1], v.shape[2]
+        out = np.empty((B, M, DV), dtype=np.float32)
+        self.v12i.ref_v12i_cpu_reference(_as_u16(q), _as_u16(k), _as_u16(v), out, B, M, Lk, KD, DV, float(scale))
+        return out
+
+    def v12i_fill_uniform(self, seed, q_shape, k_shape, v_shape):
+        q, k, v = (np.empty(s, dtype=np.uint16) for s in (q_shape, k_shape, v_shape))
+        self.v12i.ref_v12i_fill_uniform(seed, q, q.size, k, k.size, v, v.size)
+        return q.view(np.float16), k.view(np.float16), v.view(np.float16)
+
+    def v12i_rel_l2(self, a, b):
+        a = np.ascontiguousarray(a, dtype=np.float32).ravel()
+        b = np.ascontiguousarray(b, dtype=np.float32).ravel()
+        return float(self.v12i.ref_v12i_rel_l2(a, b, a.size))
+
+    def fa542_cpu_ref(self, q, k, v):
+        BH, N, D = q.shape
+        out = np.empty((BH, N, D), dtype=np.float32)
+        self.fa542.ref_fa542_cpu_ref(*(np.ascontiguousarray(x, dtype=np.float32) for x in (q, k, v)), out, BH, N, D)
+        return out
+
+    def softmax_block_flashattn_ref(self, q, k, v, scale):
+        BH, N, D = q.shape
+        out = np.empty((BH, N, D), dtype=np.float32)
+        self.sb.ref_softmax_block_flashattn_ref(*(np.ascontiguousarray(x, dtype=np.float32) for x in (q, k, v)), out,
+                                                N, D, BH, float(scale))
+        return out
+
+    def gemm_fused_cpu(self, a, b, bias, residual):
+        M, K = a.shape
+        N = b.shape[1]
+        out = np.empty((M, N), dtype=np.float32)
+        self.gemm.ref_gemm_fused_cpu(*(np.ascontiguousarray(x, dtype=np.float32) for x in (a, b, bias, residual)), out,
+                                     M, N, K)
+        return out
+
+    def gemm_fused_fill(self, seed, M, N, K):
+        a, b = np.empty((M, K), np.float32), np.empty((K, N), np.float32)
+        bias, res = np.empty((N,), np.float32), np.empty((M, N), np.float32)
+        self.gemm.ref_gemm_fused_fill(seed, a, a.size, b, b.size, bias, bias.size, res, res.size)
+        return a, b, bias, res
+
+
+class RefGpu:
+    """Launchers for the reference's own CUDA kernels (device pointers as ints)."""
+
+    def __init__(self):
+        vp = ctypes.c_void_p
+        self.v5 = RefLib("wmma_v5").L
+        self.v5.ref_wmma_v5_launch.argtypes = [vp, vp, vp, vp, c_int, c_int, c_int, c_float, vp]
+        self.v4 = RefLib("wmma_v4").L
+        self.v4.ref_wmma_v4_launch.argtypes = [vp, vp, vp, vp, c_int, c_int, c_int, c_float, vp]
+        self.v12i = RefLib("v12i").L
+        self.v12i.ref_v12i_launch.argtypes = [vp, vp, vp, vp, c_int, c_int, c_int, c_float, vp]
+        self.gemm = RefLib("gemm_fused").L
+        self.gemm.ref_gemm_fused_launch.argtypes = [vp, vp, vp, vp, vp, c_int, c_int, c_int, vp]
+        self.softmax = RefLib("softmax_naive").L
+        self.softmax.ref_softmax_naive_launch.argtypes = [vp, vp, c_int, c_int, vp]
+
+    @staticmethod
+    def _chk(rc, what):
+        if rc != 0:
+            raise RuntimeError(f"reference launcher {what} failed with cudaError {rc}")
+
+    def wmma_v5(self, q, k, v, out, scale, stream=0):
+        BH, N, D = q.shape[0] * q.shape[1], q.shape[2], q.shape[3]
+        self._chk(self.v5.ref_wmma_v5_launch(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), BH, N, D,
+                                             float(scale), stream), "wmma_v5")
+
+    def wmma_v4(self, q, k, v, out, scale, stream=0):
+        BH, N, D = q.shape[0] * q.shape[1], q.shape[2], q.shape[3]
+        self._chk(self.v4.ref_wmma_v4_launch(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), BH, N, D,
+                                             float(scale), stream), "wmma_v4")
+
+    def v12i_kernel(self, q, k, v, out, scale, stream=0):
+        B, M, L = q.shape[0], q.shape[1], k.shape[1]
+        self._chk(self.v12i.ref_v12i_launch(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, M, L,
+                                            float(scale), stream), "v12i")
+
+    def gemm_fused(self, a, b, bias, residual, out, stream=0):
+        M, K = a.shape
+        N = b.shape[1]
+        self._chk(self.gemm.ref_gemm_fused_launch(a.data_ptr(), b.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                                  residual.data_ptr() if residual is not None else None, out.data_ptr(),
+                                                  M, N, K, stream), "gemm_fused")
+
+    def softmax_naive(self, x, out, stream=0):
+        self._chk(self.softmax.ref_softmax_naive_launch(x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], stream),
+                  "softmax_naive")

@@ -1,0 +1,90 @@
+"""CPU tests of the drop-in boundary: the shared library loads, exports exactly what
+include/fa_b200.h declares, validates arguments, and refuses to compute without a B200 (no fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import flashattention_kernel_project_b200 as fa
+from flashattention_kernel_project_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(fa.lib_path()):
+        import __graft_entry__ as g
+        g.build_cuda()
+    return fa.load_library()
+
+
+def _declared_functions():
+    text = open(os.path.join(ROOT, "include", "fa_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return re.findall(r"\b([a-z_0-9]+)\s*\(", re.sub(r"#.*", "", text))
+
+
+def test_header_and_binding_agree(lib):
+    declared = set(_declared_functions())
+    assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/fa_b200.h but not exported"
+
+
+def test_no_torch_types_in_c_abi():
+    text = open(os.path.join(ROOT, "include", "fa_b200.h")).read()
+    assert "torch" not in text and "at::" not in text and 'extern "C"' in text
+
+
+def test_version_and_strerror(lib):
+    assert lib.fa_version() >= 100
+    assert b"64 or 128" in lib.fa_strerror(-2)
+    assert b"no CPU fallback" in lib.fa_strerror(-5)
+
+
+def test_argument_validation_happens_before_any_device_work(lib):
+    p = ctypes.c_void_p(0x1000)
+    assert lib.fa_forward(p, p, p, p, 1, 1, 128, 96, 0.1, None) == -2      # bad head dim
+    assert lib.fa_forward(p, p, p, p, 0, 1, 128, 64, 0.1, None) == -1      # bad shape
+    assert lib.fa_forward(None, p, p, p, 1, 1, 128, 64, 0.1, None) == -4   # null pointer
+    assert lib.fa_forward(ctypes.c_void_p(0x1004), p, p, p, 1, 1, 128, 64, 0.1, None) == -3  # misaligned
+    assert lib.fa_forward(p, p, p, p, 1, 1, 128, 64, float("nan"), None) == -7
+    assert lib.gemm_fused_epilogue(p, p, None, None, p, 128, 100, 64, None) == -3  # N % 8 != 0
+    assert lib.gemm_fused_epilogue(p, p, None, None, p, 128, 128, 0, None) == -1
+    assert lib.softmax_rows(p, None, 4, 4, None) == -4
+    assert lib.fa_forward_partial(p, p, p, p, None, p, 1, 1, 128, 128, 64, 0.1, 1, 0, None, None) == -4
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the behaviour on a box without a GPU")
+def test_compute_calls_fail_loudly_without_a_gpu(lib):
+    p = ctypes.c_void_p(0x1000)
+    assert lib.fa_forward(p, p, p, p, 1, 1, 128, 64, 0.1, None) == -5
+    assert lib.softmax_rows(p, p, 4, 4, None) == -5
+    assert lib.gemm_fused_epilogue(p, p, None, None, p, 128, 128, 64, None) == -5
+    x = np.zeros((4, 8), np.float32)
+    with pytest.raises(fa.FaError) as e:
+        fa.softmax_rows_host(x, np.empty_like(x))
+    assert e.value.code == -5
+
+
+def test_python_mirror_rejects_cpu_tensors():
+    with pytest.raises(TypeError):
+        fa.softmax_rows(torch.zeros(4, 8))
+    with pytest.raises(TypeError):
+        fa.fa_forward(torch.zeros(1, 1, 128, 64, dtype=torch.float16), torch.zeros(1, 1, 128, 64, dtype=torch.float16),
+                      torch.zeros(1, 1, 128, 64, dtype=torch.float16))
+    with pytest.raises(TypeError):
+        fa.gemm_fused_epilogue(torch.zeros(16, 16, dtype=torch.float16), torch.zeros(16, 16, dtype=torch.float16))
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "flashattention_kernel_project_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.lower() or f == "__init__.py" and "oracle" not in text, (dirpath, f)

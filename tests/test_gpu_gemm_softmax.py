@@ -1,0 +1,145 @@
+"""GPU parity tests for gemm_fused_epilogue and softmax_rows through the C ABI."""
+import numpy as np
+import pytest
+import torch
+
+from tests.oracle_lib import RefGpu, ref_available
+
+pytestmark = pytest.mark.gpu
+
+
+def _gemm_inputs(M, N, K, seed=42):
+    rng = np.random.default_rng(seed)
+    a = rng.uniform(-1, 1, (M, K)).astype(np.float16)
+    b = rng.uniform(-1, 1, (K, N)).astype(np.float16)
+    return a, b, rng.uniform(-1, 1, (N,)).astype(np.float32), rng.uniform(-1, 1, (M, N)).astype(np.float32)
+
+
+def _gemm(fa, a, b, bias, res):
+    c = fa.gemm_fused_epilogue(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(),
+                               None if bias is None else torch.from_numpy(bias).cuda(),
+                               None if res is None else torch.from_numpy(res).cuda())
+    torch.cuda.synchronize()
+    return c.cpu().numpy()
+
+
+def test_gemm_golden_vector_from_the_reference(fa, oracle, golden):
+    """mt19937(42) fixture of tensorcore_gemm_fused_epilogue.cu:178-184 through cpu_gemm_fused_ref.  The
+    reference feeds its CPU check UNROUNDED fp32 A, B while the GPU gets fp16 copies (:186-195), so this
+    comparison carries input quantisation (~sqrt(K) * 2^-11); the tight check is the next test."""
+    g = golden("gemm_fused.npz")
+    got = _gemm(fa, g["a"].astype(np.float16), g["b"].astype(np.float16), g["bias"], g["residual"])
+    assert oracle.max_abs(got, g["c"]) <= 2e-2
+    tight = oracle.gemm_fused_f16(g["a"].astype(np.float16), g["b"].astype(np.float16), g["bias"], g["residual"])
+    assert oracle.max_abs(got, tight) <= 2e-3 and oracle.rel_l2(got, tight) <= 1e-3
+
+
+@pytest.mark.parametrize("shape", [(128, 256, 64), (16, 16, 16), (1024, 1024, 1024), (1000, 1096, 520),
+                                   (129, 264, 72), (4096, 512, 2048)])
+@pytest.mark.parametrize("with_bias,with_res", [(True, True), (False, False), (True, False), (False, True)])
+def test_gemm_parity_with_oracle(fa, oracle, shape, with_bias, with_res):
+    M, N, K = shape
+    if (with_bias != with_res) and M > 200:
+        pytest.skip("nullable-operand combinations are covered on the small shapes")
+    a, b, bias, res = _gemm_inputs(M, N, K, seed=M + K)
+    bias, res = (bias if with_bias else None), (res if with_res else None)
+    got = _gemm(fa, a, b, bias, res)
+    rows = (0, M) if M <= 1024 else (M - 200, M - 72)  # sample a row block of the big case
+    ref = oracle.gemm_fused_f16(a, b, bias, res, row_begin=rows[0], row_end=rows[1])
+    sub = got[rows[0]:rows[1]]
+    assert oracle.max_abs(sub, ref) <= 2e-3 and oracle.rel_l2(sub, ref) <= 1e-3
+
+
+def test_gemm_config5a_sampled_rows_and_properties(fa, oracle):
+    """BASELINE config 5a (M=N=K=8192): 64 sampled rows through the oracle + structural properties."""
+    M = N = K = 8192
+    g = torch.Generator(device="cuda").manual_seed(42)
+    a = (torch.rand((M, K), device="cuda", generator=g) * 2 - 1).half()
+    b = (torch.rand((K, N), device="cuda", generator=g) * 2 - 1).half()
+    bias = torch.rand((N,), device="cuda", generator=g) * 2 - 1
+    res = torch.rand((M, N), device="cuda", generator=g) * 2 - 1
+    c = fa.gemm_fused_epilogue(a, b, bias, res)
+    torch.cuda.synchronize()
+    r0 = 4000
+    ref = oracle.gemm_fused_f16(a.cpu().numpy(), b.cpu().numpy(), bias.cpu().numpy(), res.cpu().numpy(),
+                                row_begin=r0, row_end=r0 + 64)
+    got = c[r0:r0 + 64].cpu().numpy()
+    # fp32 accumulation order differs (tensor-core tree vs sequential): error ~ sqrt(K) ulp of |acc| ~ 50
+    assert oracle.rel_l2(got, ref) <= 1e-3 and oracle.max_abs(got, ref) <= 2e-3
+    # epilogue identity: C - residual = ReLU(...) >= 0, and with residual = None it is exactly that
+    c0 = fa.gemm_fused_epilogue(a, b, bias, None)
+    assert (c0 >= 0).all()
+    assert torch.equal(c0 + res, c)
+    # zero A => C = ReLU(bias) + residual exactly
+    cz = fa.gemm_fused_epilogue(torch.zeros_like(a[:256]), b, bias, res[:256].contiguous())
+    assert torch.equal(cz, torch.relu(bias)[None, :] + res[:256])
+
+
+@pytest.mark.skipif(not ref_available("gemm_fused"), reason="oracle/_ref not built")
+def test_gemm_against_the_reference_kernel_on_the_same_gpu(fa, oracle):
+    a, b, bias, res = (torch.from_numpy(x).cuda() for x in _gemm_inputs(512, 768, 1024))
+    ours = fa.gemm_fused_epilogue(a, b, bias, res)
+    theirs = torch.zeros_like(ours)
+    RefGpu().gemm_fused(a, b, bias, res, theirs)
+    torch.cuda.synchronize()
+    assert oracle.max_abs(ours.cpu().numpy(), theirs.cpu().numpy()) <= 2e-3
+    assert oracle.rel_l2(ours.cpu().numpy(), theirs.cpu().numpy()) <= 1e-3
+
+
+# ------------------------------------- softmax -------------------------------------------
+def test_softmax_golden_vector(fa, oracle, golden):
+    g = golden("softmax_rows.npz")
+    p = fa.softmax_rows(torch.from_numpy(g["x"]).cuda()).cpu().numpy()
+    assert oracle.max_abs(p, g["p"]) <= 1e-6 and oracle.rel_l2(p, g["p"]) <= 1e-6
+
+
+# the reference's three softmax programs: 4096x512 (naive, hybrid), 4096x32 (warp); plus ragged/unaligned/long rows
+@pytest.mark.parametrize("rows,n", [(4096, 512), (4096, 32), (1, 1), (3, 5), (257, 1000), (64, 4096), (7, 4097),
+                                    (5, 8192), (3, 20000), (1000, 132)])
+def test_softmax_parity_with_oracle(fa, oracle, rows, n):
+    rng = np.random.default_rng(rows + n)
+    x = (rng.standard_normal((rows, n)) * 4).astype(np.float32)
+    p = fa.softmax_rows(torch.from_numpy(x).cuda()).cpu().numpy()
+    ref = oracle.softmax_rows(x)
+    # tolerance: fp32 exp (2 ulp) + reduction-order differences over n terms
+    assert oracle.max_abs(p, ref) <= 1e-6 and oracle.rel_l2(p, ref) <= 1e-5
+    assert np.allclose(p.sum(axis=1), 1.0, atol=1e-5)
+
+
+def test_softmax_reference_pattern_input_and_in_place(fa, oracle):
+    """The reference harness' input ((i % 13) - 6) * 0.1 (softmax_naive_baseline.cu:148-151), in place."""
+    rows, n = 512, 4096
+    x = (((np.arange(rows * n) % 13) - 6) * 0.1).astype(np.float32).reshape(rows, n)
+    t = torch.from_numpy(x).cuda()
+    fa.softmax_rows(t, out=t)
+    torch.cuda.synchronize()
+    assert oracle.max_abs(t.cpu().numpy(), oracle.softmax_rows(x)) <= 1e-7
+
+
+def test_softmax_config5b_full_size_properties(fa, oracle):
+    """BASELINE config 5b (16384 x 4096): sums to one, shift invariance, monotone, sampled rows vs oracle."""
+    rows, n = 16384, 4096
+    g = torch.Generator(device="cuda").manual_seed(42)
+    x = torch.rand((rows, n), device="cuda", generator=g) * 8 - 4
+    p = fa.softmax_rows(x)
+    torch.cuda.synchronize()
+    assert (p.sum(dim=1) - 1).abs().max().item() <= 1e-5
+    assert (p >= 0).all() and torch.isfinite(p).all()
+    shifted = fa.softmax_rows(x + 1.0)  # softmax(x + c) == softmax(x) up to rounding of x + c
+    assert (shifted - p).abs().max().item() <= 1e-6
+    idx = torch.tensor([0, 1, 4095, 8191, 16383], device="cuda")
+    ref = oracle.softmax_rows(x[idx].cpu().numpy())
+    assert oracle.max_abs(p[idx].cpu().numpy(), ref) <= 1e-6
+    # order preserving within a row
+    xs, order = x[7].sort()
+    assert (p[7][order].diff() >= 0).all()
+
+
+@pytest.mark.skipif(not ref_available("softmax_naive"), reason="oracle/_ref not built")
+def test_softmax_against_the_reference_kernel_on_the_same_gpu(fa, oracle):
+    x = torch.randn((1024, 4096), device="cuda") * 3
+    ours = fa.softmax_rows(x)
+    theirs = torch.zeros_like(x)
+    RefGpu().softmax_naive(x, theirs)
+    torch.cuda.synchronize()
+    assert oracle.max_abs(ours.cpu().numpy(), theirs.cpu().numpy()) <= 1e-6

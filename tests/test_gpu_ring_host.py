@@ -1,0 +1,88 @@
+"""GPU tests for fa_forward_partial (the ring / context-parallel step, chained on one GPU exactly as
+the ranks of a ring would see the shards) and for the host-buffer entry points."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _inputs(B, H, N, D, seed, std=1.0):
+    rng = np.random.default_rng(seed)
+    return tuple((rng.standard_normal((B, H, N, D)) * std).astype(np.float16) for _ in range(3))
+
+
+@pytest.mark.parametrize("D", [64, 128])
+@pytest.mark.parametrize("chunks", [[(0, 512)], [(0, 256), (256, 512)], [(0, 100), (100, 228), (228, 229), (229, 512)],
+                                    [(256, 512), (0, 256)]])
+def test_partial_chain_equals_full_attention(fa, oracle, D, chunks):
+    B, H, N = 1, 3, 512
+    q, k, v = _inputs(B, H, N, D, seed=D + len(chunks), std=1.5)
+    scale = 1.0 / np.sqrt(D)
+    tq, tk, tv = (torch.from_numpy(x).cuda() for x in (q, k, v))
+    nq = 300  # this rank's query shard is ragged on purpose
+    tq = tq[:, :, :nq].contiguous()
+    o_acc = torch.full((B, H, nq, D), float("nan"), device="cuda")  # is_first must ignore the incoming state
+    m = torch.full((B, H, nq), float("nan"), device="cuda")
+    l = torch.full((B, H, nq), float("nan"), device="cuda")
+    out = None
+    for i, (b, e) in enumerate(chunks):
+        out = fa.fa_forward_partial(tq, tk[:, :, b:e].contiguous(), tv[:, :, b:e].contiguous(), o_acc, m, l, scale,
+                                    i == 0, i == len(chunks) - 1)
+    torch.cuda.synchronize()
+    ref = oracle.attention_f16(q[:, :, :nq].reshape(B * H, nq, D), k.reshape(B * H, N, D), v.reshape(B * H, N, D), scale)
+    got = out.float().cpu().numpy().reshape(B * H, nq, D)
+    assert oracle.rel_l2(got, ref) <= 1e-3 and oracle.max_abs(got, ref) <= 2e-3
+
+
+def test_partial_state_is_the_online_softmax_state(fa, oracle):
+    """After a non-final step, (O_acc / l, m) are the exact attention / row max over the shards seen."""
+    B, H, N, D = 1, 2, 384, 64
+    q, k, v = _inputs(B, H, N, D, seed=1)
+    scale = 0.125
+    tq, tk, tv = (torch.from_numpy(x).cuda() for x in (q, k, v))
+    o_acc = torch.empty((B, H, N, D), device="cuda")
+    m = torch.empty((B, H, N), device="cuda")
+    l = torch.empty((B, H, N), device="cuda")
+    fa.fa_forward_partial(tq, tk[:, :, :200].contiguous(), tv[:, :, :200].contiguous(), o_acc, m, l, scale, True, False)
+    torch.cuda.synchronize()
+    ref = oracle.attention_f16(q.reshape(B * H, N, D), k[:, :, :200].reshape(B * H, 200, D),
+                               v[:, :, :200].reshape(B * H, 200, D), scale)
+    got = (o_acc / l[..., None]).cpu().numpy().reshape(B * H, N, D)
+    assert oracle.rel_l2(got, ref) <= 1e-3
+    s = np.einsum("bhqd,bhkd->bhqk", q.astype(np.float32), k[:, :, :200].astype(np.float32)) * scale
+    # m may lag the true max by the lazy-rescale slack (2^8 in the exp2 domain = 8 ln 2 natural units), never exceed it
+    gap = s.max(axis=-1) - m.cpu().numpy()
+    assert (gap >= -1e-3).all() and (gap <= 8 * np.log(2) + 1e-3).all()
+
+
+def test_host_buffer_entry_points(fa, oracle):
+    """The reference main() flow (H2D -> kernel -> D2H) behind one call, on pinned and pageable memory."""
+    B, H, N, D = 2, 2, 300, 128
+    q, k, v = _inputs(B, H, N, D, seed=4)
+    scale = 1.0 / np.sqrt(D)
+    ref = oracle.attention_f16(*(x.reshape(B * H, N, D) for x in (q, k, v)), scale)
+    out = np.empty_like(q)
+    fa.fa_forward_host(q, k, v, out, scale)
+    assert oracle.rel_l2(out.astype(np.float32).reshape(B * H, N, D), ref) <= 1e-3
+    pq, pk, pv = (torch.from_numpy(x).pin_memory() for x in (q, k, v))
+    pout = torch.empty_like(pq).pin_memory()
+    fa.fa_forward_host(pq, pk, pv, pout, scale)
+    assert np.array_equal(pout.numpy(), out)
+
+    rng = np.random.default_rng(0)
+    a = rng.uniform(-1, 1, (256, 128)).astype(np.float16)
+    b = rng.uniform(-1, 1, (128, 512)).astype(np.float16)
+    bias = rng.uniform(-1, 1, (512,)).astype(np.float32)
+    res = rng.uniform(-1, 1, (256, 512)).astype(np.float32)
+    c = np.empty((256, 512), np.float32)
+    fa.gemm_fused_epilogue_host(a, b, bias, res, c)
+    assert oracle.max_abs(c, oracle.gemm_fused_f16(a, b, bias, res)) <= 2e-3
+    fa.gemm_fused_epilogue_host(a, b, None, None, c)
+    assert oracle.max_abs(c, oracle.gemm_fused_f16(a, b, None, None)) <= 2e-3
+
+    x = (rng.standard_normal((100, 777)) * 3).astype(np.float32)
+    p = np.empty_like(x)
+    fa.softmax_rows_host(x, p)
+    assert oracle.max_abs(p, oracle.softmax_rows(x)) <= 1e-6
+    assert fa.launch_count() >= 5

@@ -1,0 +1,119 @@
+"""CPU tests of the CHECKER: the C restatement (oracle/fa_oracle.c) against the committed golden
+vectors (produced by the reference's own compiled functions, tests/golden/make_golden.py), against
+oracle/_ref when it is present, and against independent numpy float64 math."""
+import numpy as np
+import pytest
+
+from tests.oracle_lib import RefCpu, ref_available
+
+
+def _np_attention(q, k, v, scale):
+    s = np.einsum("bmk,btk->bmt", q.astype(np.float64), k.astype(np.float64)) * scale
+    s -= s.max(axis=-1, keepdims=True)
+    p = np.exp(s)
+    p /= p.sum(axis=-1, keepdims=True)
+    return np.einsum("bmt,btd->bmd", p, v.astype(np.float64))
+
+
+@pytest.mark.parametrize("name", ["attn_cfg1_v12i.npz", "attn_v12i_native.npz", "attn_ragged_d128.npz"])
+def test_attention_f16_matches_reference_golden_bit_exact(oracle, golden, name):
+    g = golden(name)
+    out = oracle.attention_f16(g["q"], g["k"], g["v"], float(g["scale"]))
+    assert np.array_equal(out, g["o"]), "oracle differs from the reference's cpu_reference output"
+    # the threaded path is the same arithmetic
+    assert np.array_equal(oracle.attention_f16(g["q"], g["k"], g["v"], float(g["scale"]), nthreads=1), g["o"])
+
+
+def test_attention_rows_sampling_equals_full(oracle, golden):
+    g = golden("attn_ragged_d128.npz")
+    rows = np.array([0, 1, 127, 128, 199, 200, 333, 399], dtype=np.int64)
+    out = oracle.attention_f16_rows(g["q"], g["k"], g["v"], float(g["scale"]), rows)
+    assert np.array_equal(out, g["o"].reshape(-1, g["o"].shape[-1])[rows])
+
+
+def test_attention_f32_oracles_match_golden(oracle, golden):
+    g = golden("attn_f32_oracles.npz")
+    assert np.array_equal(oracle.attention_f32_dacc(g["q"], g["k"], g["v"]), g["o_542"])
+    assert np.array_equal(oracle.attention_f32(g["q"], g["k"], g["v"], float(g["scale_block"])), g["o_block"])
+
+
+def test_oracles_agree_with_each_other_and_float64(oracle, golden):
+    # cross-check prescribed by SURVEY 8(c): v12i cpu_reference vs 5.4.2 (double accumulate) on config 1
+    g = golden("attn_cfg1_v12i.npz")
+    q, k, v = (oracle.half_to_float(g[n]).reshape(1, 128, 64) for n in ("q", "k", "v"))
+    d = oracle.attention_f32_dacc(q, k, v)  # scale = 1/sqrt(64) = 0.125, same as the fixture
+    assert oracle.rel_l2(g["o"], d) < 2e-6
+    ref64 = _np_attention(q, k, v, 0.125)
+    assert oracle.rel_l2(g["o"], ref64.astype(np.float32)) < 2e-6
+    assert oracle.max_abs(g["o"], ref64.astype(np.float32)) < 1e-6
+
+
+def test_gemm_fused_matches_golden_and_nullable_operands(oracle, golden):
+    g = golden("gemm_fused.npz")
+    assert np.array_equal(oracle.gemm_fused(g["a"], g["b"], g["bias"], g["residual"]), g["c"])
+    a, b = g["a"], g["b"]
+    plain = oracle.gemm_fused(a, b, None, None)
+    ref = np.maximum(a.astype(np.float64) @ b.astype(np.float64), 0)
+    assert np.allclose(plain, ref, atol=1e-4)
+    # epilogue order: bias -> ReLU -> residual (tensorcore_gemm_fused_epilogue.cu:109-126)
+    full = oracle.gemm_fused(a, b, g["bias"], g["residual"])
+    ref = np.maximum(a.astype(np.float64) @ b.astype(np.float64) + g["bias"], 0) + g["residual"]
+    assert np.allclose(full, ref, atol=1e-4)
+    # row-block sampling leaves other rows untouched and equals the full result on its rows
+    part = oracle.gemm_fused(a, b, g["bias"], g["residual"], row_begin=8, row_end=24)
+    assert np.array_equal(part[8:24], full[8:24]) and not part[:8].any() and not part[24:].any()
+    # fp16-operand variant == fp32 variant on half-rounded operands
+    ah, bh = a.astype(np.float16), b.astype(np.float16)
+    f16 = oracle.gemm_fused_f16(ah, bh, g["bias"], g["residual"], row_begin=8, row_end=24)
+    f32 = oracle.gemm_fused(ah.astype(np.float32), bh.astype(np.float32), g["bias"], g["residual"])
+    assert np.array_equal(f16, f32[8:24])
+
+
+def test_softmax_rows_matches_golden(oracle, golden):
+    g = golden("softmax_rows.npz")
+    p = oracle.softmax_rows(g["x"])
+    assert np.array_equal(p, g["p"])
+    assert np.allclose(p.sum(axis=1), 1.0, atol=1e-5)
+
+
+def test_half_conversions_are_exact(oracle):
+    allh = np.arange(65536, dtype=np.uint16)
+    f = oracle.half_to_float(allh)
+    want = allh.view(np.float16).astype(np.float32)
+    assert np.array_equal(f.view(np.uint32), want.view(np.uint32))
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(100000).astype(np.float32) * rng.choice([1e-8, 1e-5, 1e-3, 1, 100, 6e4], 100000).astype(np.float32)
+    x = np.concatenate([x, f[np.isfinite(f)], np.array([65519.9, 65520.0, 2.98e-8, 2.9802322e-8, 0.0, -0.0], np.float32)])
+    with np.errstate(over="ignore"):
+        assert np.array_equal(oracle.float_to_half(x), x.astype(np.float16).view(np.uint16))
+
+
+def test_metrics(oracle):
+    a = np.array([1.0, 2.0, 3.0], np.float32)
+    b = np.array([1.0, 2.5, 2.0], np.float32)
+    assert oracle.max_abs(a, b) == pytest.approx(1.0)
+    assert oracle.rel_l2(a, b) == pytest.approx(np.sqrt(1.25 / 11.25))
+    assert oracle.rel_l2(a, a) == 0.0
+
+
+@pytest.mark.skipif(not all(ref_available(n) for n in ("v12i", "fa542", "softmax_block", "gemm_fused")),
+                    reason="oracle/_ref not built (reference tree absent)")
+def test_oracle_bit_exact_against_compiled_reference(oracle):
+    """Fresh seeded inputs (not the committed fixtures) through the reference's own functions."""
+    r = RefCpu()
+    for seed, shp in [(1, (3, 40, 64)), (2, (2, 130, 128)), (3, (5, 16, 16))]:
+        q, k, v = r.v12i_fill_uniform(seed, shp, shp, shp)
+        sc = 1.0 / np.sqrt(shp[-1])
+        a, b = r.v12i_cpu_reference(q, k, v, sc), oracle.attention_f16(q, k, v, sc)
+        assert np.array_equal(a, b)
+        assert r.v12i_rel_l2(a, b) == oracle.rel_l2(a, b) == 0.0
+    # Nq != Nkv and KDIM != DV are runtime-generic in cpu_reference (:248)
+    q, _, _ = r.v12i_fill_uniform(4, (2, 7, 32), (1,), (1,))
+    _, k, v = r.v12i_fill_uniform(5, (1,), (2, 50, 32), (2, 50, 48))
+    assert np.array_equal(r.v12i_cpu_reference(q, k, v, 0.2), oracle.attention_f16(q, k, v, 0.2))
+    rng = np.random.default_rng(9)
+    qf, kf, vf = (rng.standard_normal((2, 33, 24)).astype(np.float32) for _ in range(3))
+    assert np.array_equal(r.fa542_cpu_ref(qf, kf, vf), oracle.attention_f32_dacc(qf, kf, vf))
+    assert np.array_equal(r.softmax_block_flashattn_ref(qf, kf, vf, 0.7), oracle.attention_f32(qf, kf, vf, 0.7))
+    a, b, bias, res = r.gemm_fused_fill(43, 32, 48, 64)
+    assert np.array_equal(r.gemm_fused_cpu(a, b, bias, res), oracle.gemm_fused(a, b, bias, res))

@@ -1,0 +1,117 @@
+"""CPU tests of the multi-GPU plumbing: (b,h) shard arithmetic, and the ring / context-parallel
+schedule + merge run as 2 gloo ranks with a torch fp32 implementation of the `fa_forward_partial`
+contract injected (the CUDA step itself is covered by tests/test_gpu_ring.py)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from flashattention_kernel_project_b200.sharding import ring_attention, ring_schedule, shard_range
+
+
+def test_shard_range_partitions_exactly():
+    for total in (0, 1, 7, 32, 256, 1000):
+        for world in (1, 2, 3, 4, 8):
+            spans = [shard_range(total, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [e - b for b, e in spans]
+            assert max(sizes) - min(sizes) <= 1
+    assert shard_range(256, 8, 3) == (96, 128)  # config 3: GPU g takes bh in [g*32, (g+1)*32)
+    with pytest.raises(ValueError):
+        shard_range(8, 2, 2)
+
+
+def test_ring_schedule_visits_every_shard_once():
+    for world in (1, 2, 4, 8):
+        for rank in range(world):
+            sched = ring_schedule(world, rank)
+            assert sched[0] == rank and sorted(sched) == list(range(world))
+
+
+def torch_partial_step(q, k, v, o_acc, m, l, scale, is_first, is_last, o_final):
+    """fp32 torch statement of the fa_forward_partial contract (include/fa_b200.h)."""
+    s = torch.matmul(q.float(), k.float().transpose(-1, -2)) * scale
+    m_new = s.amax(dim=-1)
+    p = torch.exp(s - m_new[..., None])
+    l_new = p.sum(dim=-1)
+    o_new = torch.matmul(p, v.float())
+    if is_first:
+        m_tot, a, b = m_new, torch.zeros_like(m_new), torch.ones_like(m_new)
+        l_acc, o_prev = torch.zeros_like(l_new), torch.zeros_like(o_new)
+    else:
+        m_tot = torch.maximum(m, m_new)
+        a, b = torch.exp(m - m_tot), torch.exp(m_new - m_tot)
+        l_acc, o_prev = l, o_acc
+    l_tot = l_acc * a + l_new * b
+    o_tot = o_prev * a[..., None] + o_new * b[..., None]
+    if is_last:
+        o_final.copy_((o_tot / l_tot[..., None]).to(o_final.dtype))
+    else:
+        o_acc.copy_(o_tot)
+        m.copy_(m_tot)
+        l.copy_(l_tot)
+    return o_final
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _ring_worker(rank, world, port, q, k, v, scale, out_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n = q.shape[2] // world
+        sl = slice(rank * n, (rank + 1) * n)
+        out = ring_attention(q[:, :, sl].contiguous(), k[:, :, sl].contiguous(), v[:, :, sl].contiguous(), scale,
+                             step_fn=torch_partial_step)
+        gathered = [torch.empty_like(out) for _ in range(world)]
+        dist.all_gather(gathered, out)  # test-only gather; the data path itself uses send/recv only
+        if rank == 0:
+            torch.save(torch.cat(gathered, dim=2), out_path)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2])
+def test_ring_attention_two_gloo_ranks_matches_oracle(tmp_path, oracle, world):
+    torch.manual_seed(0)
+    B, H, N, D = 1, 2, 64, 32
+    q, k, v = (torch.randn(B, H, N, D).half() for _ in range(3))
+    scale = 1.0 / D ** 0.5
+    out_path = str(tmp_path / "ring_out.pt")
+    mp.spawn(_ring_worker, args=(world, _free_port(), q, k, v, scale, out_path), nprocs=world, join=True)
+    got = torch.load(out_path).float().numpy().reshape(B * H, N, D)
+    ref = oracle.attention_f16(q.numpy().reshape(B * H, N, D), k.numpy().reshape(B * H, N, D),
+                               v.numpy().reshape(B * H, N, D), scale)
+    assert oracle.rel_l2(got, ref) <= 1e-3 and oracle.max_abs(got, ref) <= 2e-3  # fp16 output rounding only
+
+
+def test_ring_single_rank_is_one_full_step(oracle):
+    torch.manual_seed(1)
+    q, k, v = (torch.randn(1, 1, 40, 16).half() for _ in range(3))
+    out = ring_attention(q, k, v, 0.25, step_fn=torch_partial_step)
+    ref = oracle.attention_f16(q.numpy()[0], k.numpy()[0], v.numpy()[0], 0.25)
+    assert oracle.rel_l2(out.float().numpy()[0], ref) <= 1e-3
+
+
+def test_partial_step_chain_equals_full_attention(oracle):
+    """The merge rule itself: folding K/V shard by shard == attending to everything at once."""
+    torch.manual_seed(2)
+    B, H, N, D = 1, 1, 96, 16
+    q, k, v = (torch.randn(B, H, N, D).half() for _ in range(3))
+    o_acc = torch.zeros(B, H, N, D)
+    m, l = torch.zeros(B, H, N), torch.zeros(B, H, N)
+    out = torch.empty_like(q)
+    chunks = [(0, 32), (32, 40), (40, 96)]
+    for i, (b, e) in enumerate(chunks):
+        torch_partial_step(q, k[:, :, b:e], v[:, :, b:e], o_acc, m, l, 0.25, i == 0, i == len(chunks) - 1, out)
+    ref = oracle.attention_f16(q.numpy()[0], k.numpy()[0], v.numpy()[0], 0.25)
+    assert oracle.rel_l2(out.float().numpy()[0], ref) <= 1e-3
