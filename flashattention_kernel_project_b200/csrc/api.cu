@@ -134,6 +134,11 @@ int ensure_smem_attr(bool* done, Kernel kernel, int bytes) {
   return FA_OK;
 }
 
+#ifdef FA_TRACE
+long long* g_trace_buf = nullptr;  // developer timeline trace (scripts/trace_fa.py), not in the product build
+int g_trace_cta = 0;
+#endif
+
 // ---- attention ----------------------------------------------------------------------------
 struct FaCall {
   const void *Q, *K, *V;
@@ -181,6 +186,10 @@ int launch_fa(DeviceState* st, const FaCall& c, cudaStream_t stream) {
   p.m_state = c.m;
   p.l_state = c.l;
   p.dbg = debug_channel();
+#ifdef FA_TRACE
+  p.trace = g_trace_buf;
+  p.trace_cta = g_trace_cta;
+#endif
   const uint64_t grid = BH * static_cast<uint64_t>(p.q_blocks);
   if (grid == 0 || grid > 0x7fffffffull) return FA_ERR_BAD_SHAPE;
   fa_fwd_kernel<D><<<static_cast<unsigned>(grid), Cfg::kThreads, Cfg::kSmemBytes, stream>>>(mq, mk, mv, mo, p);
@@ -452,5 +461,12 @@ int fa_last_debug(unsigned int* words, int n) {
 }
 
 unsigned long long fa_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+#ifdef FA_TRACE
+void fa_trace_config(long long* device_buf, int cta) {
+  g_trace_buf = device_buf;
+  g_trace_cta = cta;
+}
+#endif
 
 }  // extern "C"

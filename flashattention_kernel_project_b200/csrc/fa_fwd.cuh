@@ -45,6 +45,10 @@ struct FaParams {
   float* m_state;    // FA_MODE_STATE: [bh, nq]  running max of scale*s (natural-log domain)
   float* l_state;    // FA_MODE_STATE: [bh, nq]
   DebugChannel dbg;
+#ifdef FA_TRACE
+  long long* trace;  // [6 roles][64 iterations][8 points]
+  int trace_cta;
+#endif
 };
 
 template <int D>
@@ -65,7 +69,8 @@ struct FaCfg {
   static constexpr int kOffFac = kOffKV + kStages * kTileBytes;  // float[2][128] rescale factors / final m
   static constexpr int kOffSum = kOffFac + 2 * 128 * 4;          // float[2][128] final l
   static constexpr int kOffBar = kOffSum + 2 * 128 * 4;
-  static constexpr int kNumBars = 2 + 2 * kStages + 12;
+  static constexpr int kPChunks = 4;                    // P is published to the MMA warp in 32-key chunks
+  static constexpr int kNumBars = 2 + 2 * kStages + 10 + 2 * kPChunks;
   static constexpr int kOffTmem = kOffBar + kNumBars * 8;
   static constexpr int kSmemBytes = kOffTmem + 16;
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
@@ -78,6 +83,19 @@ enum : uint32_t {
 };
 
 constexpr float kLazyRescaleTau = 8.0f;  // log2 units: P stays below 2^8, far inside fp16 range
+
+// Developer timeline trace (scripts/trace_fa.py builds a separate library with -DFA_TRACE): CTA
+// `trace_cta` stores clock64() at the role hand-off points of every K/V iteration.  Compiled out of
+// the product library.
+#ifdef FA_TRACE
+#define FA_TRACE_POINT(role, j, k)                                                                   \
+  do {                                                                                                \
+    if (p.trace != nullptr && blockIdx.x == static_cast<unsigned>(p.trace_cta) && (j) < 64)           \
+      p.trace[((role) * 64 + (j)) * 8 + (k)] = clock64();                                             \
+  } while (0)
+#else
+#define FA_TRACE_POINT(role, j, k) do { } while (0)
+#endif
 
 template <int D>
 __global__ void __launch_bounds__(512, 1)
@@ -96,8 +114,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
   uint64_t* const kv_full = bars + 2;                     // [kStages]
   uint64_t* const kv_empty = kv_full + Cfg::kStages;      // [kStages]
   uint64_t* const s_full = kv_empty + Cfg::kStages;       // [2]  MMA -> softmax : S tile ready
-  uint64_t* const p_full = s_full + 2;                    // [2]  softmax -> MMA : P tile in TMEM
-  uint64_t* const stats_full = p_full + 2;                // [2]  softmax -> correction : factors
+  uint64_t* const p_full = s_full + 2;                    // [2][kPChunks]  softmax -> MMA : P chunk in TMEM
+  uint64_t* const stats_full = p_full + 2 * Cfg::kPChunks;  // [2]  softmax -> correction : factors
   uint64_t* const corr_done = stats_full + 2;             // [2]  correction -> MMA : O rescaled
   uint64_t* const o_full = corr_done + 2;                 // [2]  MMA -> correction : last PV done
   uint64_t* const l_full = o_full + 2;                    // [2]  softmax -> correction : final l
@@ -122,12 +140,13 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
       mbar_init(&kv_empty[s], 1);
     }
     for (int i = 0; i < 2; ++i) {
+      // softmax / correction warps arrive once per warp (lane 0 after __syncwarp): count 4
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 128);
-      mbar_init(&stats_full[i], 128);
-      mbar_init(&corr_done[i], 128);
+      for (int c = 0; c < Cfg::kPChunks; ++c) mbar_init(&p_full[i * Cfg::kPChunks + c], 4);
+      mbar_init(&stats_full[i], 4);
+      mbar_init(&corr_done[i], 4);
       mbar_init(&o_full[i], 1);
-      mbar_init(&l_full[i], 128);
+      mbar_init(&l_full[i], 4);
     }
     fence_mbar_init();
   }
@@ -161,14 +180,17 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
       float l = 0.f;
 
       for (int j = 0; j < nkv_tiles; ++j) {
+        if ((warp & 3) == 0 && lane == 0) FA_TRACE_POINT(i, j, 0);
         mbar_wait(&s_full[i], j & 1, dbg, SITE_SM_SFULL, j);
         tc_fence_after();
+        if ((warp & 3) == 0 && lane == 0) FA_TRACE_POINT(i, j, 1);
         uint32_t sr[128];
         tmem_ld_x32(t_s + 0, sr + 0);
         tmem_ld_x32(t_s + 32, sr + 32);
         tmem_ld_x32(t_s + 64, sr + 64);
         tmem_ld_x32(t_s + 96, sr + 96);
         tmem_wait_ld();
+        if ((warp & 3) == 0 && lane == 0) FA_TRACE_POINT(i, j, 2);
         float* s = reinterpret_cast<float*>(sr);
         if (neg_scale) {
 #pragma unroll
@@ -203,30 +225,48 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
             m_used = m_new;
           }
           fac_smem[i * 128 + row] = fac;
-          mbar_arrive(&stats_full[i]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&stats_full[i]);
         }
 
+        if ((warp & 3) == 0 && lane == 0) FA_TRACE_POINT(i, j, 3);
+        const uint64_t c2 = pack_f32x2(c, c);
         const float neg_mc = -m_used * c;
-        float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+        const uint64_t neg_mc2 = pack_f32x2(neg_mc, neg_mc);
+        uint64_t lsum_a = pack_f32x2(0.f, 0.f), lsum_b = pack_f32x2(0.f, 0.f);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < Cfg::kPChunks; ++q) {
           uint32_t pk[16];
 #pragma unroll
           for (int k = 0; k < 32; k += 4) {
-            const float p0 = ex2_approx(fmaf(s[q * 32 + k + 0], c, neg_mc));
-            const float p1 = ex2_approx(fmaf(s[q * 32 + k + 1], c, neg_mc));
-            const float p2 = ex2_approx(fmaf(s[q * 32 + k + 2], c, neg_mc));
-            const float p3 = ex2_approx(fmaf(s[q * 32 + k + 3], c, neg_mc));
-            l0 += p0; l1 += p1; l2 += p2; l3 += p3;
+            // x = s*c - m*c for two pairs (packed FFMA2), exp2 on the MUFU, packed row-sum adds
+            const uint64_t xa = ffma2(pack_f32x2(s[q * 32 + k + 0], s[q * 32 + k + 1]), c2, neg_mc2);
+            const uint64_t xb = ffma2(pack_f32x2(s[q * 32 + k + 2], s[q * 32 + k + 3]), c2, neg_mc2);
+            float x0, x1, x2, x3;
+            unpack_f32x2(xa, x0, x1);
+            unpack_f32x2(xb, x2, x3);
+            const float p0 = ex2_approx(x0), p1 = ex2_approx(x1), p2 = ex2_approx(x2), p3 = ex2_approx(x3);
+            lsum_a = fadd2(lsum_a, pack_f32x2(p0, p1));
+            lsum_b = fadd2(lsum_b, pack_f32x2(p2, p3));
             pk[k / 2 + 0] = pack_half2(p0, p1);
             pk[k / 2 + 1] = pack_half2(p2, p3);
           }
-          tmem_st_x16(t_s + q * 16, pk);  // P (fp16 pairs) overwrites columns [0,64) of its own S
+          // P (fp16 pairs) overwrites columns [0,64) of its own S; each 32-key chunk is published as
+          // soon as it is in TMEM so the PV MMAs of the first chunks overlap the exps of the later ones
+          tmem_st_x16(t_s + q * 16, pk);
+          tmem_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[i * Cfg::kPChunks + q]);
+          if (q == 0 && (warp & 3) == 0 && lane == 0) FA_TRACE_POINT(i, j, 4);
         }
-        tmem_wait_st();
-        tc_fence_before();
-        mbar_arrive(&p_full[i]);
-        l += (l0 + l1) + (l2 + l3);
+        if ((warp & 3) == 0 && lane == 0) FA_TRACE_POINT(i, j, 5);
+        {
+          float a0, a1, b0, b1;
+          unpack_f32x2(fadd2(lsum_a, lsum_b), a0, a1);
+          (void)b0; (void)b1;
+          l += a0 + a1;
+        }
       }
 
       // final statistics for the epilogue
@@ -237,7 +277,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
         if (nkv_tiles >= 2) mbar_wait(&corr_done[i], (nkv_tiles - 2) & 1, dbg, SITE_SM_CORR, i);
         fac_smem[i * 128 + row] = neg_scale ? -m_used : m_used;  // raw-score max, true sign
       }
-      mbar_arrive(&l_full[i]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&l_full[i]);
     }
   } else if (warp < 12) {
     // ========================= correction + epilogue warpgroup ========================
@@ -249,6 +290,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
     for (int j = 1; j < nkv_tiles; ++j) {
       for (int i = 0; i < ntile; ++i) {
         mbar_wait(&stats_full[i], (j - 1) & 1, dbg, SITE_CO_STATS, j);
+        if (warp == 8 && lane == 0) FA_TRACE_POINT(2 + i, j, 0);
         const float fac = fac_smem[i * 128 + row];
         if (__any_sync(0xffffffffu, fac != 1.f)) {
           tc_fence_after();
@@ -265,7 +307,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
           tmem_wait_st();
         }
         tc_fence_before();
-        mbar_arrive(&corr_done[i]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&corr_done[i]);
+        if (warp == 8 && lane == 0) FA_TRACE_POINT(2 + i, j, 1);
       }
     }
 
@@ -368,34 +412,52 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
     if (warp == 8 && lane == 0) tma_store_wait_all<0>();
   } else if (warp == 12) {
     // ================================ MMA issuer ======================================
+    // The whole warp walks the schedule (uniform control flow: every lane waits on the barriers);
+    // one lane chosen by elect.sync issues the tcgen05 instructions.  (Putting the loop under
+    // `if (lane == 0)` makes ptxas wrap every UTCHMMA in a per-thread serialisation loop.)
     setmaxnreg_dec<48>();
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc_qk = umma_idesc_f16(128, 128, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_f16(128, D, 0, 1);
       const uint32_t q_addr = smem_u32(q_smem);
       const uint32_t kv_addr = smem_u32(kv_smem);
 
-      auto issue_qk = [&](int i, int slot) {
+      // S_i = Q_i K^T, then signal s_full[i]; optionally release the K slot afterwards
+      auto issue_qk = [&](int i, int slot, uint64_t* release) {
         const uint32_t a0 = q_addr + i * Cfg::kTileBytes;
         const uint32_t b0 = kv_addr + slot * Cfg::kTileBytes;
         const uint32_t d = tmem_base + (i == 0 ? Cfg::kColS0 : Cfg::kColS1);
+        if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < D / 16; ++ks) {
-          const uint32_t off = (ks >> 2) * Cfg::kBoxBytes + (ks & 3) * 32;
-          umma_ss(d, umma_desc_sw128(a0 + off, 16, 1024), umma_desc_sw128(b0 + off, 16, 1024), idesc_qk,
-                  ks > 0 ? 1u : 0u);
+          for (int ks = 0; ks < D / 16; ++ks) {
+            const uint32_t off = (ks >> 2) * Cfg::kBoxBytes + (ks & 3) * 32;
+            umma_ss(d, umma_desc_sw128(a0 + off, 16, 1024), umma_desc_sw128(b0 + off, 16, 1024), idesc_qk,
+                    ks > 0 ? 1u : 0u);
+          }
+          umma_commit(&s_full[i]);
+          if (release != nullptr) umma_commit(release);
         }
+        __syncwarp();
       };
-      auto issue_pv = [&](int i, int slot, bool accumulate) {
+      // O_i (+)= P_i[:, 32c .. 32c+32) V[32c .. 32c+32, :]  (two 16-key MMAs per published P chunk)
+      auto issue_pv_chunk = [&](int i, int slot, int c, bool accumulate) {
         const uint32_t b0 = kv_addr + slot * Cfg::kTileBytes;
         const uint32_t d = tmem_base + (i == 0 ? Cfg::kColO0 : Cfg::kColO1);
         const uint32_t a = tmem_base + (i == 0 ? Cfg::kColS0 : Cfg::kColS1);
+        if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < Cfg::kKT / 16; ++ks) {
-          // V tile: rows = keys (128 B of head dim each): MN-major B operand, 16 keys = 2048 B per step
-          umma_ts(d, a + ks * 8, umma_desc_sw128(b0 + ks * 2048, Cfg::kBoxBytes, 1024), idesc_pv,
-                  (accumulate || ks > 0) ? 1u : 0u);
+          for (int kk = 0; kk < 2; ++kk) {
+            const int ks = c * 2 + kk;
+            // V tile: rows = keys (128 B of head dim each): MN-major B operand, 16 keys = 2048 B per step
+            umma_ts(d, a + ks * 8, umma_desc_sw128(b0 + ks * 2048, Cfg::kBoxBytes, 1024), idesc_pv,
+                    (accumulate || ks > 0) ? 1u : 0u);
+          }
         }
+        __syncwarp();
+      };
+      auto commit_to = [&](uint64_t* bar) {
+        if (elect_one()) umma_commit(bar);
+        __syncwarp();
       };
       auto slot_of = [](int t) { return t % Cfg::kStages; };
       auto par_of = [](int t) { return (t / Cfg::kStages) & 1; };
@@ -404,47 +466,56 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
       mbar_wait(&q_full[0], 0, dbg, SITE_MMA_QFULL, 0);
       mbar_wait(&kv_full[slot_of(0)], par_of(0), dbg, SITE_MMA_KVFULL, 0);
       tc_fence_after();
-      issue_qk(0, slot_of(0));
-      umma_commit(&s_full[0]);
+      issue_qk(0, slot_of(0), ntile == 2 ? nullptr : &kv_empty[slot_of(0)]);
       if (ntile == 2) {
         mbar_wait(&q_full[1], 0, dbg, SITE_MMA_QFULL, 1);
         tc_fence_after();
-        issue_qk(1, slot_of(0));
-        umma_commit(&s_full[1]);
+        issue_qk(1, slot_of(0), &kv_empty[slot_of(0)]);
       }
-      umma_commit(&kv_empty[slot_of(0)]);
 
       for (int j = 0; j < nkv_tiles; ++j) {
         const int tv = 2 * j + 1, tk = 2 * j + 2;
         const bool more = (j + 1 < nkv_tiles);
         mbar_wait(&kv_full[slot_of(tv)], par_of(tv), dbg, SITE_MMA_KVFULL, tv);
         for (int i = 0; i < ntile; ++i) {
-          mbar_wait(&p_full[i], j & 1, dbg, SITE_MMA_PFULL, j);
+          if (lane == 0) FA_TRACE_POINT(4 + i, j, 0);
           if (j > 0) mbar_wait(&corr_done[i], (j - 1) & 1, dbg, SITE_MMA_CORR, j);
-          tc_fence_after();
-          issue_pv(i, slot_of(tv), j > 0);
-          if (!more) umma_commit(&o_full[i]);
-          if (more) {
+#pragma unroll
+          for (int c = 0; c < Cfg::kPChunks; ++c) {
+            mbar_wait(&p_full[i * Cfg::kPChunks + c], j & 1, dbg, SITE_MMA_PFULL, j);
+            tc_fence_after();
+            if (c == 0 && lane == 0) FA_TRACE_POINT(4 + i, j, 1);
+            issue_pv_chunk(i, slot_of(tv), c, j > 0);
+          }
+          if (lane == 0) FA_TRACE_POINT(4 + i, j, 3);
+          const bool last_tile = (i == ntile - 1);
+          if (!more) {
+            commit_to(&o_full[i]);
+            if (last_tile) commit_to(&kv_empty[slot_of(tv)]);
+          } else {
             if (i == 0) {
               mbar_wait(&kv_full[slot_of(tk)], par_of(tk), dbg, SITE_MMA_KVFULL, tk);
               tc_fence_after();
             }
-            issue_qk(i, slot_of(tk));
-            umma_commit(&s_full[i]);
+            if (last_tile) commit_to(&kv_empty[slot_of(tv)]);  // V(j) is free once every PV(j) has run
+            issue_qk(i, slot_of(tk), last_tile ? &kv_empty[slot_of(tk)] : nullptr);
+            if (lane == 0) FA_TRACE_POINT(4 + i, j, 4);
           }
         }
-        umma_commit(&kv_empty[slot_of(tv)]);
-        if (more) umma_commit(&kv_empty[slot_of(tk)]);
       }
     }
   } else if (warp == 13) {
     // ================================ TMA producer ====================================
     setmaxnreg_dec<48>();
-    if (lane == 0) {
+    {
       auto load_tile = [&](const CUtensorMap* map, uint8_t* dst, uint64_t* bar, int row0, uint64_t hint) {
-        mbar_arrive_expect_tx(bar, Cfg::kTileBytes);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(bar, Cfg::kTileBytes);
 #pragma unroll
-        for (int b = 0; b < Cfg::kBoxes; ++b) tma_load_3d(dst + b * Cfg::kBoxBytes, map, bar, b * 64, row0, bh, hint);
+          for (int b = 0; b < Cfg::kBoxes; ++b)
+            tma_load_3d(dst + b * Cfg::kBoxBytes, map, bar, b * 64, row0, bh, hint);
+        }
+        __syncwarp();
       };
       load_tile(&mapQ, q_smem, &q_full[0], q0, kEvictFirst);
       const int total = 2 * nkv_tiles;

@@ -99,7 +99,8 @@ gemm_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 
   if (warp == 0) {
     // ------------------------------- TMA producer -----------------------------------
-    if (lane == 0) {
+    // whole warp walks the schedule; the lane chosen by elect.sync issues (see fa_fwd.cuh)
+    {
       int it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         int mb, nb;
@@ -110,18 +111,21 @@ gemm_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           mbar_wait(&empty[s], par ^ 1, dbg, SITE_G_EMPTY, it);
           uint8_t* const a_dst = smem + s * Cfg::kStageBytes;
           uint8_t* const b_dst = a_dst + Cfg::kABytes;
-          mbar_arrive_expect_tx(&full[s], Cfg::kStageBytes);
-          tma_load_2d(a_dst, &mapA, &full[s], kb * Cfg::kBK, mb * Cfg::kBM, kEvictNormal);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&full[s], Cfg::kStageBytes);
+            tma_load_2d(a_dst, &mapA, &full[s], kb * Cfg::kBK, mb * Cfg::kBM, kEvictNormal);
 #pragma unroll
-          for (int b = 0; b < Cfg::kBN / 64; ++b)
-            tma_load_2d(b_dst + b * Cfg::kBBoxBytes, &mapB, &full[s], nb * Cfg::kBN + b * 64, kb * Cfg::kBK,
-                        kEvictNormal);
+            for (int b = 0; b < Cfg::kBN / 64; ++b)
+              tma_load_2d(b_dst + b * Cfg::kBBoxBytes, &mapB, &full[s], nb * Cfg::kBN + b * 64, kb * Cfg::kBK,
+                          kEvictNormal);
+          }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
     // -------------------------------- MMA issuer -------------------------------------
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = umma_idesc_f16(Cfg::kBM, Cfg::kBN, 0, 1);
       int it = 0, local = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
@@ -137,14 +141,17 @@ gemm_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           tc_fence_after();
           const uint32_t a0 = smem_u32(smem + s * Cfg::kStageBytes);
           const uint32_t b0 = a0 + Cfg::kABytes;
+          if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < Cfg::kBK / 16; ++ks) {
-            umma_ss(d, umma_desc_sw128(a0 + ks * 32, 16, 1024),
-                    umma_desc_sw128(b0 + ks * 2048, Cfg::kBBoxBytes, 1024), idesc, (kb | ks) ? 1u : 0u);
+            for (int ks = 0; ks < Cfg::kBK / 16; ++ks) {
+              umma_ss(d, umma_desc_sw128(a0 + ks * 32, 16, 1024),
+                      umma_desc_sw128(b0 + ks * 2048, Cfg::kBBoxBytes, 1024), idesc, (kb | ks) ? 1u : 0u);
+            }
+            umma_commit(&empty[s]);
+            if (kb == num_kb - 1) umma_commit(&tfull[acc]);
           }
-          umma_commit(&empty[s]);
+          __syncwarp();
         }
-        umma_commit(&tfull[acc]);
       }
     }
   } else if (warp >= 4) {

@@ -1,0 +1,39 @@
+"""Developer tool: bitwise run-to-run and batch-vs-slice comparison of fa_forward at config-3 size."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import flashattention_kernel_project_b200 as fa
+
+B, H, N, D = 8, 32, 4096, 128
+g = torch.Generator(device="cuda").manual_seed(3)
+q, k, v = ((torch.rand((B, H, N, D), device="cuda", generator=g) * 2 - 1).half() for _ in range(3))
+sc = D ** -0.5
+a = fa.fa_forward(q, k, v, sc)
+b = fa.fa_forward(q, k, v, sc)
+torch.cuda.synchronize()
+diff = (a != b)
+print("full vs full: mismatching elements", int(diff.sum()), "of", a.numel())
+if diff.any():
+    idx = diff.nonzero()
+    print(" first mismatches (b,h,row,col):", idx[:10].tolist())
+    rows = idx[:, :3].unique(dim=0)
+    print(" rows affected:", rows.shape[0], "row%128 histogram:", torch.bincount(rows[:, 2] % 128, minlength=128).tolist())
+    print(" max abs diff", (a.float() - b.float()).abs().max().item())
+s = fa.fa_forward(q[:1, :2].contiguous(), k[:1, :2].contiguous(), v[:1, :2].contiguous(), sc)
+torch.cuda.synchronize()
+d2 = (s != a[:1, :2])
+print("slice vs full: mismatching", int(d2.sum()), "of", s.numel())
+if d2.any():
+    idx = d2.nonzero()
+    print(" first:", idx[:10].tolist(), "max abs", (s.float() - a[:1, :2].float()).abs().max().item())
+    rows = idx[:, :3].unique(dim=0)
+    print(" rows affected:", rows.shape[0], "cols hist(32-col chunks):", torch.bincount(idx[:, 3] // 32, minlength=4).tolist())
+s2 = fa.fa_forward(q[:1, :2].contiguous(), k[:1, :2].contiguous(), (v[:1, :2] * 2).contiguous(), sc)
+torch.cuda.synchronize()
+d3 = (s2.float() != s.float() * 2)
+print("2V vs 2*O (slice): mismatching", int(d3.sum()))
+if d3.any():
+    idx = d3.nonzero()
+    print(" first:", idx[:10].tolist())
+    i0 = tuple(idx[0].tolist())
+    print(" values", s2[i0].item(), s[i0].item() * 2)

@@ -32,7 +32,8 @@ def test_partial_chain_equals_full_attention(fa, oracle, D, chunks):
     torch.cuda.synchronize()
     ref = oracle.attention_f16(q[:, :, :nq].reshape(B * H, nq, D), k.reshape(B * H, N, D), v.reshape(B * H, N, D), scale)
     got = out.float().cpu().numpy().reshape(B * H, nq, D)
-    assert oracle.rel_l2(got, ref) <= 1e-3 and oracle.max_abs(got, ref) <= 2e-3
+    # N(0, 1.5) inputs give |O| up to ~4: the absolute bound scales with it (see tests/test_gpu_attention._check)
+    assert oracle.rel_l2(got, ref) <= 1e-3 and oracle.max_abs(got, ref) <= 2e-3 * max(1.0, float(np.abs(ref).max()))
 
 
 def test_partial_state_is_the_online_softmax_state(fa, oracle):
