@@ -22,8 +22,8 @@
 // CTA = 512 threads = 4 warpgroups, one CTA per SM, 256 query rows per CTA as two 128-row tiles
 // that ping-pong on the tensor pipe:
 //   WG0 (warps 0-3)   softmax of Q tile 0        WG1 (warps 4-7)  softmax of Q tile 1
-//   WG2 (warps 8-11)  correction + epilogue      WG3: warp 12 = MMA issuer (1 thread),
-//                                                     warp 13 = TMA producer (1 thread)
+//   WG2 (warps 8-11)  correction + epilogue      WG3: warp 12 = MMA issuer (one elected lane),
+//                                                     warp 13 = TMA producer
 // TMEM (512 columns x 128 lanes x 32 bit): S0 @0, S1 @128, O0 @256, O1 @256+D.  P (fp16, two per
 // column) overwrites the first 64 columns of its own S.
 #pragma once
@@ -69,8 +69,8 @@ struct FaCfg {
   static constexpr int kOffFac = kOffKV + kStages * kTileBytes;  // float[2][128] rescale factors / final m
   static constexpr int kOffSum = kOffFac + 2 * 128 * 4;          // float[2][128] final l
   static constexpr int kOffBar = kOffSum + 2 * 128 * 4;
-  static constexpr int kPChunks = 4;                    // P is published to the MMA warp in 32-key chunks
-  static constexpr int kNumBars = 2 + 2 * kStages + 10 + 2 * kPChunks;
+  static constexpr int kPChunks = 2;                    // P is published in two chunks: keys [0,96), [96,128)
+  static constexpr int kNumBars = 2 + 2 * kStages + 8 + 2 * kPChunks;
   static constexpr int kOffTmem = kOffBar + kNumBars * 8;
   static constexpr int kSmemBytes = kOffTmem + 16;
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
@@ -78,11 +78,15 @@ struct FaCfg {
 
 // mbarrier wait sites (reported through the debug channel on a timeout)
 enum : uint32_t {
-  SITE_TMA_EMPTY = 1, SITE_MMA_QFULL, SITE_MMA_KVFULL, SITE_MMA_PFULL, SITE_MMA_CORR,
+  SITE_TMA_EMPTY = 1, SITE_MMA_QFULL, SITE_MMA_KVFULL, SITE_MMA_PFULL,
   SITE_SM_SFULL, SITE_SM_CORR, SITE_CO_STATS, SITE_CO_LFULL, SITE_CO_OFULL
 };
 
 constexpr float kLazyRescaleTau = 8.0f;  // log2 units: P stays below 2^8, far inside fp16 range
+#ifndef FA_POLY_PER8
+#define FA_POLY_PER8 4
+#endif
+constexpr int kPolyPer8 = FA_POLY_PER8;  // of every 8 keys (outside the speculative head) this many use the FMA-pipe exp2
 
 // Developer timeline trace (scripts/trace_fa.py builds a separate library with -DFA_TRACE): CTA
 // `trace_cta` stores clock64() at the role hand-off points of every K/V iteration.  Compiled out of
@@ -116,8 +120,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
   uint64_t* const s_full = kv_empty + Cfg::kStages;       // [2]  MMA -> softmax : S tile ready
   uint64_t* const p_full = s_full + 2;                    // [2][kPChunks]  softmax -> MMA : P chunk in TMEM
   uint64_t* const stats_full = p_full + 2 * Cfg::kPChunks;  // [2]  softmax -> correction : factors
-  uint64_t* const corr_done = stats_full + 2;             // [2]  correction -> MMA : O rescaled
-  uint64_t* const o_full = corr_done + 2;                 // [2]  MMA -> correction : last PV done
+  uint64_t* const o_full = stats_full + 2;                // [2]  MMA -> correction : last PV done
   uint64_t* const l_full = o_full + 2;                    // [2]  softmax -> correction : final l
   uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(smem + Cfg::kOffTmem);
 
@@ -142,9 +145,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
     for (int i = 0; i < 2; ++i) {
       // softmax / correction warps arrive once per warp (lane 0 after __syncwarp): count 4
       mbar_init(&s_full[i], 1);
-      for (int c = 0; c < Cfg::kPChunks; ++c) mbar_init(&p_full[i * Cfg::kPChunks + c], 4);
+      // chunk 0 also collects the correction warps: "P ready" and "O rescaled" are one wait for the MMA warp
+      for (int c = 0; c < Cfg::kPChunks; ++c) mbar_init(&p_full[i * Cfg::kPChunks + c], c == 0 ? 8 : 4);
       mbar_init(&stats_full[i], 4);
-      mbar_init(&corr_done[i], 4);
       mbar_init(&o_full[i], 1);
       mbar_init(&l_full[i], 4);
     }
@@ -179,17 +182,26 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
       float m_used = -INFINITY;  // running max of (sign-folded) raw scores the exponent refers to
       float l = 0.f;
 
+#ifdef FA_ABL_NOSOFTWG  // developer ablation (with FA_ABL_NOWAITP): softmax warps idle, only MMA + TMA run
+      for (int j = nkv_tiles; j < nkv_tiles; ++j) {
+#else
       for (int j = 0; j < nkv_tiles; ++j) {
+#endif
         if ((warp & 3) == 0 && lane == 0) FA_TRACE_POINT(i, j, 0);
         mbar_wait(&s_full[i], j & 1, dbg, SITE_SM_SFULL, j);
         tc_fence_after();
         if ((warp & 3) == 0 && lane == 0) FA_TRACE_POINT(i, j, 1);
         uint32_t sr[128];
+#ifdef FA_ABL_NOLDST  // developer ablation: no TMEM traffic from the softmax warps
+#pragma unroll
+        for (int k = 0; k < 128; ++k) sr[k] = __float_as_uint(static_cast<float>(k + lane) * 0.01f);
+#else
         tmem_ld_x32(t_s + 0, sr + 0);
         tmem_ld_x32(t_s + 32, sr + 32);
         tmem_ld_x32(t_s + 64, sr + 64);
         tmem_ld_x32(t_s + 96, sr + 96);
         tmem_wait_ld();
+#endif
         if ((warp & 3) == 0 && lane == 0) FA_TRACE_POINT(i, j, 2);
         float* s = reinterpret_cast<float*>(sr);
         if (neg_scale) {
@@ -202,8 +214,24 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
           for (int k = 0; k < 128; ++k)
             if (k >= valid) s[k] = -INFINITY;
         }
+        // ---- speculative head: the exps of the first 32 keys are computed against the STALE running
+        // max while the 64-instruction row-max chain runs in their shadow (MUFU and ALU pipes overlap).
+        // The lazy-rescale rule makes the stale max the common case; when a row does need a new max
+        // (always at j == 0, where the stale max is -inf) its 32 exps are simply redone.
+        const uint64_t c2 = pack_f32x2(c, c);
+        float neg_mc = -m_used * c;
+        uint64_t neg_mc2 = pack_f32x2(neg_mc, neg_mc);
+        float pe[32];
+#pragma unroll
+        for (int k = 0; k < 32; k += 2) {
+          float x0, x1;
+          unpack_f32x2(ffma2(pack_f32x2(s[k], s[k + 1]), c2, neg_mc2), x0, x1);
+          pe[k] = ex2_approx(x0);
+          pe[k + 1] = ex2_approx(x1);
+        }
         // four independent 3-input max chains, one per 32-column quarter
         float mx0 = s[0], mx1 = s[32], mx2 = s[64], mx3 = s[96];
+#ifndef FA_ABL_NOMAX
 #pragma unroll
         for (int k = 1; k < 31; k += 2) {
           mx0 = fmax3(mx0, s[k], s[k + 1]);
@@ -213,58 +241,87 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
         }
         mx0 = fmax3(mx0, s[31], s[63]);
         mx2 = fmax3(mx2, s[95], s[127]);
+#endif
         const float m_new = fmaxf(fmax3(mx0, mx1, mx2), fmaxf(mx3, m_used));
+        if ((warp & 3) == 0 && lane == 0) FA_TRACE_POINT(i, j, 6);
 
-        if (j == 0) {
-          m_used = m_new;
-        } else {
-          float fac = 1.f;
-          if ((m_new - m_used) * c > kLazyRescaleTau) {  // lazy: tolerate a stale max up to 2^tau
-            fac = ex2_approx((m_used - m_new) * c);
+        // lazy rescale: keep the stale max while the true max exceeds it by at most 2^tau
+        const bool need = (m_new - m_used) * c > kLazyRescaleTau;  // j == 0: (x - -inf) = +inf -> true
+        float fac = 1.f;
+        if (__any_sync(0xffffffffu, need)) {
+          if (need) {
+            fac = ex2_approx((m_used - m_new) * c);  // j == 0: exp2(-inf) = 0, and l is 0
             l *= fac;
             m_used = m_new;
+            neg_mc = -m_used * c;
+            neg_mc2 = pack_f32x2(neg_mc, neg_mc);
+#pragma unroll
+            for (int k = 0; k < 32; k += 2) {
+              float x0, x1;
+              unpack_f32x2(ffma2(pack_f32x2(s[k], s[k + 1]), c2, neg_mc2), x0, x1);
+              pe[k] = ex2_approx(x0);
+              pe[k + 1] = ex2_approx(x1);
+            }
           }
+        }
+        if (j > 0) {
           fac_smem[i * 128 + row] = fac;
           __syncwarp();
           if (lane == 0) mbar_arrive(&stats_full[i]);
         }
-
         if ((warp & 3) == 0 && lane == 0) FA_TRACE_POINT(i, j, 3);
-        const uint64_t c2 = pack_f32x2(c, c);
-        const float neg_mc = -m_used * c;
-        const uint64_t neg_mc2 = pack_f32x2(neg_mc, neg_mc);
+
+        // ---- exps, packed row sums, fp16 P written back over S; P is published to the MMA warp in two
+        // chunks (keys [0,96) then [96,128)) so most PV MMAs overlap the tail of the softmax
         uint64_t lsum_a = pack_f32x2(0.f, 0.f), lsum_b = pack_f32x2(0.f, 0.f);
+        const float cy = c * (1.f / 128.f);                 // y = sat(s*cy + by) encodes x = 128*y - 120
+        const float by = (neg_mc + 120.f) * (1.f / 128.f);
 #pragma unroll
-        for (int q = 0; q < Cfg::kPChunks; ++q) {
+        for (int q = 0; q < 4; ++q) {
           uint32_t pk[16];
 #pragma unroll
           for (int k = 0; k < 32; k += 4) {
-            // x = s*c - m*c for two pairs (packed FFMA2), exp2 on the MUFU, packed row-sum adds
-            const uint64_t xa = ffma2(pack_f32x2(s[q * 32 + k + 0], s[q * 32 + k + 1]), c2, neg_mc2);
-            const uint64_t xb = ffma2(pack_f32x2(s[q * 32 + k + 2], s[q * 32 + k + 3]), c2, neg_mc2);
-            float x0, x1, x2, x3;
-            unpack_f32x2(xa, x0, x1);
-            unpack_f32x2(xb, x2, x3);
-            const float p0 = ex2_approx(x0), p1 = ex2_approx(x1), p2 = ex2_approx(x2), p3 = ex2_approx(x3);
+            float p0, p1, p2, p3;
+            if (q == 0) {
+              p0 = pe[k]; p1 = pe[k + 1]; p2 = pe[k + 2]; p3 = pe[k + 3];
+            } else {
+              // of every 8 keys, kPolyPer8 take the FMA-pipe polynomial and the rest the MUFU
+              float x0, x1, x2, x3;
+              if ((k & 7) < kPolyPer8) {
+                exp2_poly_pair(pack_f32x2(ffma_sat(s[q * 32 + k + 0], cy, by), ffma_sat(s[q * 32 + k + 1], cy, by)), p0, p1);
+              } else {
+                unpack_f32x2(ffma2(pack_f32x2(s[q * 32 + k + 0], s[q * 32 + k + 1]), c2, neg_mc2), x0, x1);
+                p0 = ex2_approx(x0); p1 = ex2_approx(x1);
+              }
+              if (((k + 2) & 7) < kPolyPer8) {
+                exp2_poly_pair(pack_f32x2(ffma_sat(s[q * 32 + k + 2], cy, by), ffma_sat(s[q * 32 + k + 3], cy, by)), p2, p3);
+              } else {
+                unpack_f32x2(ffma2(pack_f32x2(s[q * 32 + k + 2], s[q * 32 + k + 3]), c2, neg_mc2), x2, x3);
+                p2 = ex2_approx(x2); p3 = ex2_approx(x3);
+              }
+            }
             lsum_a = fadd2(lsum_a, pack_f32x2(p0, p1));
             lsum_b = fadd2(lsum_b, pack_f32x2(p2, p3));
             pk[k / 2 + 0] = pack_half2(p0, p1);
             pk[k / 2 + 1] = pack_half2(p2, p3);
           }
-          // P (fp16 pairs) overwrites columns [0,64) of its own S; each 32-key chunk is published as
-          // soon as it is in TMEM so the PV MMAs of the first chunks overlap the exps of the later ones
-          tmem_st_x16(t_s + q * 16, pk);
-          tmem_wait_st();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&p_full[i * Cfg::kPChunks + q]);
-          if (q == 0 && (warp & 3) == 0 && lane == 0) FA_TRACE_POINT(i, j, 4);
+#ifdef FA_ABL_NOLDST
+          if (pk[0] == 0x12345678u && pk[7] == 0x9abcdef0u) tmem_st_x16(t_s + q * 16, pk);  // never true: keeps the math alive
+#else
+          tmem_st_x16(t_s + q * 16, pk);  // P (fp16 pairs) overwrites columns [0,64) of its own S
+#endif
+          if (q >= 2) {
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_full[i * Cfg::kPChunks + (q - 2)]);
+            if (q == 2 && (warp & 3) == 0 && lane == 0) FA_TRACE_POINT(i, j, 4);
+          }
         }
         if ((warp & 3) == 0 && lane == 0) FA_TRACE_POINT(i, j, 5);
         {
-          float a0, a1, b0, b1;
+          float a0, a1;
           unpack_f32x2(fadd2(lsum_a, lsum_b), a0, a1);
-          (void)b0; (void)b1;
           l += a0 + a1;
         }
       }
@@ -273,8 +330,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
       sum_smem[i * 128 + row] = l;
       if (p.mode == FA_MODE_STATE) {
         // fac_smem doubles as the final-max slot; the correction WG has consumed its last factor
-        // once corr_done completed its last phase.
-        if (nkv_tiles >= 2) mbar_wait(&corr_done[i], (nkv_tiles - 2) & 1, dbg, SITE_SM_CORR, i);
+        // once the last phase of p_full[chunk 0] (which its warps also arrive on) has completed.
+        mbar_wait(&p_full[i * Cfg::kPChunks], (nkv_tiles - 1) & 1, dbg, SITE_SM_CORR, i);
         fac_smem[i * 128 + row] = neg_scale ? -m_used : m_used;  // raw-score max, true sign
       }
       __syncwarp();
@@ -287,7 +344,14 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
     const int row = wq * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(wq * 32) << 16;
 
+    // j == 0: nothing to rescale (PV(0) overwrites O); the arrival only balances the barrier count
+    if (lane == 0)
+      for (int i = 0; i < ntile; ++i) mbar_arrive(&p_full[i * Cfg::kPChunks]);
+#ifdef FA_ABL_NOSOFTWG
+    for (int j = nkv_tiles; j < nkv_tiles; ++j) {
+#else
     for (int j = 1; j < nkv_tiles; ++j) {
+#endif
       for (int i = 0; i < ntile; ++i) {
         mbar_wait(&stats_full[i], (j - 1) & 1, dbg, SITE_CO_STATS, j);
         if (warp == 8 && lane == 0) FA_TRACE_POINT(2 + i, j, 0);
@@ -308,7 +372,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&corr_done[i]);
+        if (lane == 0) mbar_arrive(&p_full[i * Cfg::kPChunks]);
         if (warp == 8 && lane == 0) FA_TRACE_POINT(2 + i, j, 1);
       }
     }
@@ -415,6 +479,10 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
     // The whole warp walks the schedule (uniform control flow: every lane waits on the barriers);
     // one lane chosen by elect.sync issues the tcgen05 instructions.  (Putting the loop under
     // `if (lane == 0)` makes ptxas wrap every UTCHMMA in a per-thread serialisation loop.)
+    // Static order: QK0(0) QK1(0) | PV0(j) QK0(j+1) PV1(j) QK1(j+1) | ...  -- tcgen05 ops of one thread
+    // execute in order, which gives PV_i(j) before QK_i(j+1) (whose S overwrites P_i) for free.
+    // (Two issuing warps, one per tile, were measured slower: the tiles' MMAs interleave on the pipe
+    //  and lengthen each tile's S -> softmax -> P chain.)
     setmaxnreg_dec<48>();
     {
       constexpr uint32_t idesc_qk = umma_idesc_f16(128, 128, 0, 0);
@@ -422,41 +490,43 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
       const uint32_t q_addr = smem_u32(q_smem);
       const uint32_t kv_addr = smem_u32(kv_smem);
 
-      // S_i = Q_i K^T, then signal s_full[i]; optionally release the K slot afterwards
+      // S_i = Q_i K^T; signals s_full[i]; optionally releases the K slot afterwards
       auto issue_qk = [&](int i, int slot, uint64_t* release) {
         const uint32_t a0 = q_addr + i * Cfg::kTileBytes;
         const uint32_t b0 = kv_addr + slot * Cfg::kTileBytes;
         const uint32_t d = tmem_base + (i == 0 ? Cfg::kColS0 : Cfg::kColS1);
         if (elect_one()) {
+#ifndef FA_ABL_NOQK
 #pragma unroll
           for (int ks = 0; ks < D / 16; ++ks) {
             const uint32_t off = (ks >> 2) * Cfg::kBoxBytes + (ks & 3) * 32;
             umma_ss(d, umma_desc_sw128(a0 + off, 16, 1024), umma_desc_sw128(b0 + off, 16, 1024), idesc_qk,
                     ks > 0 ? 1u : 0u);
           }
+#endif
           umma_commit(&s_full[i]);
           if (release != nullptr) umma_commit(release);
         }
         __syncwarp();
       };
-      // O_i (+)= P_i[:, 32c .. 32c+32) V[32c .. 32c+32, :]  (two 16-key MMAs per published P chunk)
-      auto issue_pv_chunk = [&](int i, int slot, int c, bool accumulate) {
+      // O_i (+)= P_i[:, chunk c] V[chunk c, :]: chunk 0 = keys [0,96) (six 16-key MMAs), chunk 1 = [96,128)
+      auto issue_pv_chunk = [&](int i, int slot, int c, bool accumulate, uint64_t* done0, uint64_t* done1) {
         const uint32_t b0 = kv_addr + slot * Cfg::kTileBytes;
         const uint32_t d = tmem_base + (i == 0 ? Cfg::kColO0 : Cfg::kColO1);
         const uint32_t a = tmem_base + (i == 0 ? Cfg::kColS0 : Cfg::kColS1);
         if (elect_one()) {
+          const int ks_begin = (c == 0) ? 0 : 6, ks_end = (c == 0) ? 6 : 8;
+#ifndef FA_ABL_NOPV
 #pragma unroll
-          for (int kk = 0; kk < 2; ++kk) {
-            const int ks = c * 2 + kk;
+          for (int ks = ks_begin; ks < ks_end; ++ks) {
             // V tile: rows = keys (128 B of head dim each): MN-major B operand, 16 keys = 2048 B per step
             umma_ts(d, a + ks * 8, umma_desc_sw128(b0 + ks * 2048, Cfg::kBoxBytes, 1024), idesc_pv,
                     (accumulate || ks > 0) ? 1u : 0u);
           }
+#endif
+          if (done0 != nullptr) umma_commit(done0);
+          if (done1 != nullptr) umma_commit(done1);
         }
-        __syncwarp();
-      };
-      auto commit_to = [&](uint64_t* bar) {
-        if (elect_one()) umma_commit(bar);
         __syncwarp();
       };
       auto slot_of = [](int t) { return t % Cfg::kStages; };
@@ -476,28 +546,29 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
       for (int j = 0; j < nkv_tiles; ++j) {
         const int tv = 2 * j + 1, tk = 2 * j + 2;
         const bool more = (j + 1 < nkv_tiles);
+        if (lane == 0) FA_TRACE_POINT(4, j, 5);
         mbar_wait(&kv_full[slot_of(tv)], par_of(tv), dbg, SITE_MMA_KVFULL, tv);
+        if (more) mbar_wait(&kv_full[slot_of(tk)], par_of(tk), dbg, SITE_MMA_KVFULL, tk);
+        if (lane == 0) FA_TRACE_POINT(4, j, 6);
         for (int i = 0; i < ntile; ++i) {
-          if (lane == 0) FA_TRACE_POINT(4 + i, j, 0);
-          if (j > 0) mbar_wait(&corr_done[i], (j - 1) & 1, dbg, SITE_MMA_CORR, j);
-#pragma unroll
-          for (int c = 0; c < Cfg::kPChunks; ++c) {
-            mbar_wait(&p_full[i * Cfg::kPChunks + c], j & 1, dbg, SITE_MMA_PFULL, j);
-            tc_fence_after();
-            if (c == 0 && lane == 0) FA_TRACE_POINT(4 + i, j, 1);
-            issue_pv_chunk(i, slot_of(tv), c, j > 0);
-          }
-          if (lane == 0) FA_TRACE_POINT(4 + i, j, 3);
           const bool last_tile = (i == ntile - 1);
-          if (!more) {
-            commit_to(&o_full[i]);
-            if (last_tile) commit_to(&kv_empty[slot_of(tv)]);
-          } else {
-            if (i == 0) {
-              mbar_wait(&kv_full[slot_of(tk)], par_of(tk), dbg, SITE_MMA_KVFULL, tk);
-              tc_fence_after();
-            }
-            if (last_tile) commit_to(&kv_empty[slot_of(tv)]);  // V(j) is free once every PV(j) has run
+          uint64_t* const p_full_i = &p_full[i * Cfg::kPChunks];
+          if (lane == 0) FA_TRACE_POINT(4 + i, j, 0);
+#ifndef FA_ABL_NOWAITP
+          mbar_wait(&p_full_i[0], j & 1, dbg, SITE_MMA_PFULL, j);  // P chunk 0 written and O rescaled
+#endif
+          tc_fence_after();
+          if (lane == 0) FA_TRACE_POINT(4 + i, j, 1);
+          issue_pv_chunk(i, slot_of(tv), 0, j > 0, nullptr, nullptr);
+#ifndef FA_ABL_NOWAITP
+          mbar_wait(&p_full_i[1], j & 1, dbg, SITE_MMA_PFULL, j);
+#endif
+          tc_fence_after();
+          // V(j) is released by the commit that follows its last reader; the final PV also signals o_full
+          issue_pv_chunk(i, slot_of(tv), 1, true, last_tile ? &kv_empty[slot_of(tv)] : nullptr,
+                         more ? nullptr : &o_full[i]);
+          if (lane == 0) FA_TRACE_POINT(4 + i, j, 3);
+          if (more) {
             issue_qk(i, slot_of(tk), last_tile ? &kv_empty[slot_of(tk)] : nullptr);
             if (lane == 0) FA_TRACE_POINT(4 + i, j, 4);
           }
@@ -523,6 +594,13 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
         const int slot = t % Cfg::kStages;
         const int par = (t / Cfg::kStages) & 1;
         mbar_wait(&kv_empty[slot], par ^ 1, dbg, SITE_TMA_EMPTY, t);
+#ifdef FA_ABL_NOFILL  // developer ablation: after the ring has been filled once, stop moving data
+        if (t >= Cfg::kStages) {
+          if (elect_one()) mbar_arrive(&kv_full[slot]);
+          __syncwarp();
+          continue;
+        }
+#endif
         load_tile((t & 1) ? &mapV : &mapK, kv_smem + slot * Cfg::kTileBytes, &kv_full[slot], (t >> 1) * Cfg::kKT,
                   kEvictLast);
         if (t == 0 && ntile == 2) load_tile(&mapQ, q_smem + Cfg::kTileBytes, &q_full[1], q0 + 128, kEvictFirst);

@@ -293,11 +293,17 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t M, uint32_t N, ui
 
 // ---------------------------------- small math -----------------------------------------
 __device__ __forceinline__ float ex2_approx(float x) {
+#ifdef FA_ABL_NOEXP  // developer ablation builds only (scripts/bench_variant.py); results are wrong by design
+  return x;
+#endif
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
+#ifdef FA_ABL_NOCVT
+  return __float_as_uint(lo) ^ __float_as_uint(hi);
+#endif
   uint32_t r;
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
@@ -331,6 +337,43 @@ __device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
   uint64_t d;
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
+}
+
+__device__ __forceinline__ uint64_t ffma2_rm(uint64_t a, uint64_t b, uint64_t c) {  // round toward -inf
+  uint64_t d;
+  asm("fma.rm.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t fsub2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float ffma_sat(float a, float b, float c) {  // clamp(a*b + c, 0, 1)
+  float d;
+  asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
+// exp2 on the FMA pipes for a packed pair, taking load off the 16-lane/clk MUFU (the co-critical
+// resource of attention at head dim 128).  Input y in [0,1] encodes x = 128*y - 120 in [-120, 8]
+// (the caller produces y with one saturating FFMA, which also clamps -inf / very negative scores).
+//   t = 128*y - 120 + 1.5*2^23, rounded toward -inf  -> mantissa of t holds floor(x)
+//   f = x - floor(x) in [0,1);  2^f ~ 1 + c1 f + c2 f^2 + c3 f^3  (max rel. error 8.6e-5, below the
+//   fp16 rounding of P);  result = bits(2^f) + (floor(x) << 23).
+__device__ __forceinline__ void exp2_poly_pair(uint64_t y2, float& p0, float& p1) {
+  const uint64_t k128 = pack_f32x2(128.f, 128.f);
+  const uint64_t kOff = pack_f32x2(12582792.f, 12582792.f);  // 1.5*2^23 - 120 (exact)
+  const uint64_t t2 = ffma2_rm(y2, k128, kOff);
+  const uint64_t f2 = ffma2(y2, k128, fsub2(kOff, t2));       // (128y - 120) - floor(.)
+  uint64_t r2 = ffma2(f2, pack_f32x2(0.07706617564f, 0.07706617564f), pack_f32x2(0.22764593363f, 0.22764593363f));
+  r2 = ffma2(r2, f2, pack_f32x2(0.69511657953f, 0.69511657953f));
+  r2 = ffma2(r2, f2, pack_f32x2(1.f, 1.f));
+  float t0, t1, r0, r1;
+  unpack_f32x2(t2, t0, t1);
+  unpack_f32x2(r2, r0, r1);
+  p0 = __uint_as_float(__float_as_uint(r0) + (__float_as_uint(t0) << 23));
+  p1 = __uint_as_float(__float_as_uint(r1) + (__float_as_uint(t1) << 23));
 }
 
 template <int NREG>

@@ -7,7 +7,8 @@ import sys
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-lib = ctypes.CDLL(os.path.join(ROOT, "flashattention_kernel_project_b200", "libfa_b200_trace.so"))
+libname = sys.argv[2] if len(sys.argv) > 2 else "libfa_b200_trace.so"
+lib = ctypes.CDLL(os.path.join(ROOT, "flashattention_kernel_project_b200", libname))
 lib.fa_forward.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int] * 4 + [ctypes.c_float, ctypes.c_void_p]
 lib.fa_trace_config.argtypes = [ctypes.c_void_p, ctypes.c_int]
 B, H, N, D = 8, 32, 4096, 128
@@ -15,6 +16,7 @@ cta = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
 q, k, v = ((torch.rand((B, H, N, D), device="cuda") * 2 - 1).half() for _ in range(3))
 o = torch.empty_like(q)
 trace = torch.zeros((6, 64, 8), dtype=torch.int64, device="cuda")
+brief = len(sys.argv) > 3
 run = lambda: lib.fa_forward(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), B, H, N, D, D ** -0.5, None)
 for _ in range(3):
     assert run() == 0
@@ -25,9 +27,9 @@ torch.cuda.synchronize()
 t = trace.cpu()
 t0 = int(t[t > 0].min())
 names = ["soft0", "soft1", "corr0", "corr1", "mma0", "mma1"]
-pts = {"soft": ["wait_s", "s_ready", "ld_done", "max_done", "exp_done", "p_arrived"],
+pts = {"soft": ["wait_s", "s_ready", "ld_done", "stats_done", "chunk0_pub", "p_arrived", "max_done"],
        "corr": ["stats_seen", "corr_arrived"], "mma": ["wait_p", "p_seen", "corr_seen", "pv_issued", "qk_issued"]}
-for j in range(0, 32):
+for j in range(0, 0 if brief else 32):
     print(f"--- iteration {j}")
     for r, name in enumerate(names):
         labels = pts[name[:4] if name[:4] in pts else name[:3]]
@@ -38,11 +40,16 @@ import statistics as st
 def col(r, k):
     return [int(t[r, j, k]) for j in range(8, 29)]
 for i in (0, 1):
-    s_ready, ld, mx, ex, pa = (col(i, k) for k in (1, 2, 3, 4, 5))
+    s_ready, ld, sd, c0, pa, mx = (col(i, k) for k in (1, 2, 3, 4, 5, 6))
     per = [b - a for a, b in zip(s_ready, s_ready[1:])]
-    print(f"soft{i}: period={st.mean(per):.0f}  ld={st.mean(b - a for a, b in zip(s_ready, ld)):.0f} "
-          f"max={st.mean(b - a for a, b in zip(ld, mx)):.0f} exp={st.mean(b - a for a, b in zip(mx, ex)):.0f} "
-          f"st+arrive={st.mean(b - a for a, b in zip(ex, pa)):.0f} wait_for_S={st.mean(b - a for a, b in zip(pa, s_ready[1:])):.0f}")
-    p_seen, c_seen, pv, qk = (col(4 + i, k) for k in (1, 2, 3, 4))
-    print(f"mma{i}: p_arrived->p_seen={st.mean(b - a for a, b in zip(pa, p_seen)):.0f} pv_issue={st.mean(b - a for a, b in zip(c_seen, pv)):.0f} "
-          f"qk_issue={st.mean(b - a for a, b in zip(pv, qk)):.0f} qk_issued->s_ready(next)={st.mean(b - a for a, b in zip(qk, s_ready[1:])):.0f}")
+    d = lambda x, y: st.mean(b - a for a, b in zip(x, y))
+    print(f"soft{i}: period={st.mean(per):.0f}  ld={d(s_ready, ld):.0f} max={d(ld, mx):.0f} stats={d(mx, sd):.0f} "
+          f"chunk0={d(sd, c0):.0f} chunks1-3={d(c0, pa):.0f} wait_for_S={d(pa, s_ready[1:]):.0f}")
+    p_seen, pv, qk = (col(4 + i, k) for k in (1, 3, 4))
+    print(f"mma{i}: chunk0_pub->seen={d(c0, p_seen):.0f} last_pub->pv_all_issued={d(pa, pv):.0f} "
+          f"pv_issued->qk_issued={d(pv, qk):.0f} qk_issued->s_ready(next)={d(qk, s_ready[1:]):.0f}")
+
+top = [int(t[4, j, 5]) for j in range(8, 29)]
+aft = [int(t[4, j, 6]) for j in range(8, 29)]
+if all(x > 0 for x in top):
+    print(f"mma warp: iteration period={st.mean(b - a for a, b in zip(top, top[1:])):.0f} kv_full waits={st.mean(b - a for a, b in zip(top, aft)):.0f}")
