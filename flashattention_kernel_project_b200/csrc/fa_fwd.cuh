@@ -84,9 +84,13 @@ enum : uint32_t {
 
 constexpr float kLazyRescaleTau = 8.0f;  // log2 units: P stays below 2^8, far inside fp16 range
 #ifndef FA_POLY_PER8
-#define FA_POLY_PER8 4
+#define FA_POLY_PER8 0
 #endif
-constexpr int kPolyPer8 = FA_POLY_PER8;  // of every 8 keys (outside the speculative head) this many use the FMA-pipe exp2
+// Of every 8 keys (outside the speculative head) this many take the FMA-pipe polynomial exp2 instead of the
+// MUFU.  Measured on B200 (config 3): 0 -> 1210, 2 -> 1218, 4 -> 1150 TFLOP/s -- with one softmax warp per SM
+// sub-partition and tile, a warp's own MUFU issue stall and its FMA work do not overlap, so the offload does
+// not pay yet; it is kept as a build-time knob for the schedules of later rounds.
+constexpr int kPolyPer8 = FA_POLY_PER8;
 
 // Developer timeline trace (scripts/trace_fa.py builds a separate library with -DFA_TRACE): CTA
 // `trace_cta` stores clock64() at the role hand-off points of every K/V iteration.  Compiled out of
@@ -182,26 +186,17 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
       float m_used = -INFINITY;  // running max of (sign-folded) raw scores the exponent refers to
       float l = 0.f;
 
-#ifdef FA_ABL_NOSOFTWG  // developer ablation (with FA_ABL_NOWAITP): softmax warps idle, only MMA + TMA run
-      for (int j = nkv_tiles; j < nkv_tiles; ++j) {
-#else
       for (int j = 0; j < nkv_tiles; ++j) {
-#endif
         if ((warp & 3) == 0 && lane == 0) FA_TRACE_POINT(i, j, 0);
         mbar_wait(&s_full[i], j & 1, dbg, SITE_SM_SFULL, j);
         tc_fence_after();
         if ((warp & 3) == 0 && lane == 0) FA_TRACE_POINT(i, j, 1);
         uint32_t sr[128];
-#ifdef FA_ABL_NOLDST  // developer ablation: no TMEM traffic from the softmax warps
-#pragma unroll
-        for (int k = 0; k < 128; ++k) sr[k] = __float_as_uint(static_cast<float>(k + lane) * 0.01f);
-#else
         tmem_ld_x32(t_s + 0, sr + 0);
         tmem_ld_x32(t_s + 32, sr + 32);
         tmem_ld_x32(t_s + 64, sr + 64);
         tmem_ld_x32(t_s + 96, sr + 96);
         tmem_wait_ld();
-#endif
         if ((warp & 3) == 0 && lane == 0) FA_TRACE_POINT(i, j, 2);
         float* s = reinterpret_cast<float*>(sr);
         if (neg_scale) {
@@ -231,7 +226,6 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
         }
         // four independent 3-input max chains, one per 32-column quarter
         float mx0 = s[0], mx1 = s[32], mx2 = s[64], mx3 = s[96];
-#ifndef FA_ABL_NOMAX
 #pragma unroll
         for (int k = 1; k < 31; k += 2) {
           mx0 = fmax3(mx0, s[k], s[k + 1]);
@@ -241,7 +235,6 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
         }
         mx0 = fmax3(mx0, s[31], s[63]);
         mx2 = fmax3(mx2, s[95], s[127]);
-#endif
         const float m_new = fmaxf(fmax3(mx0, mx1, mx2), fmaxf(mx3, m_used));
         if ((warp & 3) == 0 && lane == 0) FA_TRACE_POINT(i, j, 6);
 
@@ -305,11 +298,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
             pk[k / 2 + 0] = pack_half2(p0, p1);
             pk[k / 2 + 1] = pack_half2(p2, p3);
           }
-#ifdef FA_ABL_NOLDST
-          if (pk[0] == 0x12345678u && pk[7] == 0x9abcdef0u) tmem_st_x16(t_s + q * 16, pk);  // never true: keeps the math alive
-#else
           tmem_st_x16(t_s + q * 16, pk);  // P (fp16 pairs) overwrites columns [0,64) of its own S
-#endif
           if (q >= 2) {
             tmem_wait_st();
             tc_fence_before();
@@ -347,11 +336,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
     // j == 0: nothing to rescale (PV(0) overwrites O); the arrival only balances the barrier count
     if (lane == 0)
       for (int i = 0; i < ntile; ++i) mbar_arrive(&p_full[i * Cfg::kPChunks]);
-#ifdef FA_ABL_NOSOFTWG
-    for (int j = nkv_tiles; j < nkv_tiles; ++j) {
-#else
     for (int j = 1; j < nkv_tiles; ++j) {
-#endif
       for (int i = 0; i < ntile; ++i) {
         mbar_wait(&stats_full[i], (j - 1) & 1, dbg, SITE_CO_STATS, j);
         if (warp == 8 && lane == 0) FA_TRACE_POINT(2 + i, j, 0);
@@ -496,14 +481,12 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
         const uint32_t b0 = kv_addr + slot * Cfg::kTileBytes;
         const uint32_t d = tmem_base + (i == 0 ? Cfg::kColS0 : Cfg::kColS1);
         if (elect_one()) {
-#ifndef FA_ABL_NOQK
 #pragma unroll
           for (int ks = 0; ks < D / 16; ++ks) {
             const uint32_t off = (ks >> 2) * Cfg::kBoxBytes + (ks & 3) * 32;
             umma_ss(d, umma_desc_sw128(a0 + off, 16, 1024), umma_desc_sw128(b0 + off, 16, 1024), idesc_qk,
                     ks > 0 ? 1u : 0u);
           }
-#endif
           umma_commit(&s_full[i]);
           if (release != nullptr) umma_commit(release);
         }
@@ -516,14 +499,12 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
         const uint32_t a = tmem_base + (i == 0 ? Cfg::kColS0 : Cfg::kColS1);
         if (elect_one()) {
           const int ks_begin = (c == 0) ? 0 : 6, ks_end = (c == 0) ? 6 : 8;
-#ifndef FA_ABL_NOPV
 #pragma unroll
           for (int ks = ks_begin; ks < ks_end; ++ks) {
             // V tile: rows = keys (128 B of head dim each): MN-major B operand, 16 keys = 2048 B per step
             umma_ts(d, a + ks * 8, umma_desc_sw128(b0 + ks * 2048, Cfg::kBoxBytes, 1024), idesc_pv,
                     (accumulate || ks > 0) ? 1u : 0u);
           }
-#endif
           if (done0 != nullptr) umma_commit(done0);
           if (done1 != nullptr) umma_commit(done1);
         }
@@ -554,15 +535,11 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
           const bool last_tile = (i == ntile - 1);
           uint64_t* const p_full_i = &p_full[i * Cfg::kPChunks];
           if (lane == 0) FA_TRACE_POINT(4 + i, j, 0);
-#ifndef FA_ABL_NOWAITP
           mbar_wait(&p_full_i[0], j & 1, dbg, SITE_MMA_PFULL, j);  // P chunk 0 written and O rescaled
-#endif
           tc_fence_after();
           if (lane == 0) FA_TRACE_POINT(4 + i, j, 1);
           issue_pv_chunk(i, slot_of(tv), 0, j > 0, nullptr, nullptr);
-#ifndef FA_ABL_NOWAITP
           mbar_wait(&p_full_i[1], j & 1, dbg, SITE_MMA_PFULL, j);
-#endif
           tc_fence_after();
           // V(j) is released by the commit that follows its last reader; the final PV also signals o_full
           issue_pv_chunk(i, slot_of(tv), 1, true, last_tile ? &kv_empty[slot_of(tv)] : nullptr,
@@ -594,13 +571,6 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
         const int slot = t % Cfg::kStages;
         const int par = (t / Cfg::kStages) & 1;
         mbar_wait(&kv_empty[slot], par ^ 1, dbg, SITE_TMA_EMPTY, t);
-#ifdef FA_ABL_NOFILL  // developer ablation: after the ring has been filled once, stop moving data
-        if (t >= Cfg::kStages) {
-          if (elect_one()) mbar_arrive(&kv_full[slot]);
-          __syncwarp();
-          continue;
-        }
-#endif
         load_tile((t & 1) ? &mapV : &mapK, kv_smem + slot * Cfg::kTileBytes, &kv_full[slot], (t >> 1) * Cfg::kKT,
                   kEvictLast);
         if (t == 0 && ntile == 2) load_tile(&mapQ, q_smem + Cfg::kTileBytes, &q_full[1], q0 + 128, kEvictFirst);

@@ -293,17 +293,11 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t M, uint32_t N, ui
 
 // ---------------------------------- small math -----------------------------------------
 __device__ __forceinline__ float ex2_approx(float x) {
-#ifdef FA_ABL_NOEXP  // developer ablation builds only (scripts/bench_variant.py); results are wrong by design
-  return x;
-#endif
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
-#ifdef FA_ABL_NOCVT
-  return __float_as_uint(lo) ^ __float_as_uint(hi);
-#endif
   uint32_t r;
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
