@@ -1,0 +1,66 @@
+"""Multi-GPU GPU tests (skipped on a single-GPU box; run with `gpurun --gpus 2`): (b,h) sharding with no
+collective, and the ring / context-parallel path with NCCL send/recv + fa_forward_partial."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, mode, q, k, v, scale, out_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import flashattention_kernel_project_b200 as fa
+        B, H, N, D = q.shape
+        if mode == "bh":
+            # flat (b,h) units, contiguous slices, no communication on the data path
+            b0, b1 = fa.shard_range(B * H, world, rank)
+            qs, ks, vs = (x.view(1, B * H, N, D)[:, b0:b1].contiguous().cuda() for x in (q, k, v))
+            out = fa.fa_forward(qs, ks, vs, scale)
+            torch.cuda.synchronize()
+            gathered = [torch.empty((1, e - b, N, D), dtype=torch.float16, device="cuda")
+                        for b, e in (fa.shard_range(B * H, world, r) for r in range(world))]
+            dist.all_gather(gathered, out)  # test-only
+            full = torch.cat(gathered, dim=1).view(B, H, N, D)
+        else:
+            n = N // world
+            sl = slice(rank * n, (rank + 1) * n)
+            out = fa.ring_attention(q[:, :, sl].contiguous().cuda(), k[:, :, sl].contiguous().cuda(),
+                                    v[:, :, sl].contiguous().cuda(), scale)
+            torch.cuda.synchronize()
+            gathered = [torch.empty_like(out) for _ in range(world)]
+            dist.all_gather(gathered, out)  # test-only
+            full = torch.cat(gathered, dim=2)
+        if rank == 0:
+            torch.save(full.cpu(), out_path)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+@pytest.mark.parametrize("mode,shape", [("bh", (2, 5, 640, 128)), ("ring", (1, 4, 1024, 128)), ("ring", (2, 2, 768, 64))])
+def test_two_gpu_paths_match_oracle(tmp_path, oracle, mode, shape):
+    B, H, N, D = shape
+    rng = np.random.default_rng(5)
+    q, k, v = (torch.from_numpy(rng.standard_normal((B, H, N, D)).astype(np.float16)) for _ in range(3))
+    scale = 1.0 / np.sqrt(D)
+    out_path = str(tmp_path / "out.pt")
+    mp.spawn(_worker, args=(2, _free_port(), mode, q, k, v, scale, out_path), nprocs=2, join=True)
+    got = torch.load(out_path).float().numpy().reshape(B * H, N, D)
+    ref = oracle.attention_f16(q.numpy().reshape(B * H, N, D), k.numpy().reshape(B * H, N, D),
+                               v.numpy().reshape(B * H, N, D), scale)
+    assert oracle.rel_l2(got, ref) <= 1e-3
+    assert oracle.max_abs(got, ref) <= 2e-3 * max(1.0, float(np.abs(ref).max()))
