@@ -299,6 +299,49 @@ def run_ours(args):
     return 0
 
 
+def reference_gpu_kernels(torch, dev):
+    """The reference's own CUDA kernels (compiled unmodified into oracle/_ref, test infrastructure) timed on
+    this GPU next to ours, as the north-star asks: WMMA v5 at config 2 and on a (b,h) slice of config 3,
+    the fused WMMA GEMM at 8192^3, the naive softmax at 16384 x 4096.  Never on the product path."""
+    try:
+        from tests.oracle_lib import RefGpu, ref_available
+        if not all(ref_available(n) for n in ("wmma_v5", "gemm_fused", "softmax_naive")):
+            return {"unavailable": "oracle/_ref not built"}
+        ref = RefGpu()
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": str(e)[:100]}
+    out = {}
+
+    def timeit(fn, iters):
+        fn()
+        torch.cuda.synchronize()
+        return time_loop(torch, fn, iters) / iters
+
+    B, H, N, D = 4, 16, 1024, 64
+    q, k, v = ((torch.rand((B, H, N, D), device=dev) * 2 - 1).half() for _ in range(3))
+    o = torch.zeros((B, H, N, D), device=dev)
+    ms = timeit(lambda: ref.wmma_v5(q, k, v, o, 0.125), 20)
+    out["wmma_v5_cfg2_B4_H16_N1024_D64"] = {"ms": ms, "tflops": flops(B, H, N, D) / ms / 1e9}
+    B, H, N, D = 1, 8, 4096, 128  # 8 of the 256 (b,h) pairs of config 3 (the kernel is linear in BH)
+    q, k, v = ((torch.rand((B, H, N, D), device=dev) * 2 - 1).half() for _ in range(3))
+    o = torch.zeros((B, H, N, D), device=dev)
+    ms = timeit(lambda: ref.wmma_v5(q, k, v, o, D ** -0.5), 3)
+    out["wmma_v5_cfg3_slice_BH8_N4096_D128"] = {"ms": ms, "tflops": flops(B, H, N, D) / ms / 1e9}
+    del q, k, v, o
+    M = 8192
+    a = (torch.rand((M, M), device=dev) * 2 - 1).half()
+    b = (torch.rand((M, M), device=dev) * 2 - 1).half()
+    bias, res, c = torch.rand((M,), device=dev), torch.rand((M, M), device=dev), torch.empty((M, M), device=dev)
+    ms = timeit(lambda: ref.gemm_fused(a, b, bias, res, c), 2)
+    out["wmma_gemm_fused_8192"] = {"ms": ms, "tflops": 2.0 * M ** 3 / ms / 1e9}
+    del a, b, res, c
+    x = torch.randn((16384, 4096), device=dev)
+    p = torch.empty_like(x)
+    ms = timeit(lambda: ref.softmax_naive(x, p), 10)
+    out["softmax_naive_16384x4096"] = {"us": ms * 1e3, "gbs": 2.0 * x.numel() * 4 / ms / 1e6}
+    return out
+
+
 def extras(torch, fa, dev, peaks):
     """Companion entry points and the other single-GPU BASELINE configs (reported, not the headline)."""
     out = {}
@@ -342,6 +385,18 @@ def extras(torch, fa, dev, peaks):
     ms = time_loop(torch, f, 50) / 50
     gbs = 2.0 * x.numel() * 4 / ms / 1e6
     out["softmax_16384x4096"] = {"us": ms * 1e3, "gbs": gbs, "frac_of_measured_hbm": gbs / peaks["hbm_gbs"]}
+    del x, p
+    # config 4 on one GPU: B=1,H=32,N=65536,D=128 (70.4 TFLOP per launch)
+    B, H, N, D = 1, 32, 65536, 128
+    q, k, v = ((torch.rand((B, H, N, D), device=dev) * 2 - 1).half() for _ in range(3))
+    o = torch.empty_like(q)
+    f = lambda: fa.fa_forward(q, k, v, D ** -0.5, out=o)
+    f()
+    torch.cuda.synchronize()
+    ms = time_loop(torch, f, 2) / 2
+    out["attn_cfg4_B1_H32_N65536_D128_1gpu"] = {"ms": ms, "tflops": flops(B, H, N, D) / ms / 1e9}
+    del q, k, v, o
+    out["reference_gpu_kernels_on_this_gpu"] = reference_gpu_kernels(torch, dev)
     return out
 
 

@@ -92,6 +92,18 @@ constexpr float kLazyRescaleTau = 8.0f;  // log2 units: P stays below 2^8, far i
 // not pay yet; it is kept as a build-time knob for the schedules of later rounds.
 constexpr int kPolyPer8 = FA_POLY_PER8;
 
+// Schedule knobs (build-time; defaults are the measured best on B200)
+#ifndef FA_SPEC_KEYS
+#define FA_SPEC_KEYS 32   // exps computed against the stale max in the shadow of the row-max chain
+#endif
+#ifndef FA_SPLIT_GROUPS
+#define FA_SPLIT_GROUPS 6  // P is published after this many 16-key groups, then after all 8
+#endif
+constexpr int kSpecKeys = FA_SPEC_KEYS;
+constexpr int kSplitGroups = FA_SPLIT_GROUPS;
+static_assert(kSpecKeys % 16 == 0 && kSpecKeys >= 16 && kSpecKeys <= 64, "speculative head is whole 16-key groups");
+static_assert(kSplitGroups >= 1 && kSplitGroups <= 7, "first publication covers 1..7 groups of 16 keys");
+
 // Developer timeline trace (scripts/trace_fa.py builds a separate library with -DFA_TRACE): CTA
 // `trace_cta` stores clock64() at the role hand-off points of every K/V iteration.  Compiled out of
 // the product library.
@@ -216,9 +228,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
         const uint64_t c2 = pack_f32x2(c, c);
         float neg_mc = -m_used * c;
         uint64_t neg_mc2 = pack_f32x2(neg_mc, neg_mc);
-        float pe[32];
+        float pe[kSpecKeys];
 #pragma unroll
-        for (int k = 0; k < 32; k += 2) {
+        for (int k = 0; k < kSpecKeys; k += 2) {
           float x0, x1;
           unpack_f32x2(ffma2(pack_f32x2(s[k], s[k + 1]), c2, neg_mc2), x0, x1);
           pe[k] = ex2_approx(x0);
@@ -226,6 +238,13 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
         }
         // four independent 3-input max chains, one per 32-column quarter
         float mx0 = s[0], mx1 = s[32], mx2 = s[64], mx3 = s[96];
+#ifdef FA_MAX2  // 2-input max chains (experiment)
+#pragma unroll
+        for (int k = 1; k < 32; ++k) {
+          mx0 = fmaxf(mx0, s[k]); mx1 = fmaxf(mx1, s[32 + k]); mx2 = fmaxf(mx2, s[64 + k]); mx3 = fmaxf(mx3, s[96 + k]);
+        }
+        const float m_new = fmaxf(fmaxf(mx0, mx1), fmaxf(fmaxf(mx2, mx3), m_used));
+#else
 #pragma unroll
         for (int k = 1; k < 31; k += 2) {
           mx0 = fmax3(mx0, s[k], s[k + 1]);
@@ -236,6 +255,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
         mx0 = fmax3(mx0, s[31], s[63]);
         mx2 = fmax3(mx2, s[95], s[127]);
         const float m_new = fmaxf(fmax3(mx0, mx1, mx2), fmaxf(mx3, m_used));
+#endif
         if ((warp & 3) == 0 && lane == 0) FA_TRACE_POINT(i, j, 6);
 
         // lazy rescale: keep the stale max while the true max exceeds it by at most 2^tau
@@ -249,7 +269,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
             neg_mc = -m_used * c;
             neg_mc2 = pack_f32x2(neg_mc, neg_mc);
 #pragma unroll
-            for (int k = 0; k < 32; k += 2) {
+            for (int k = 0; k < kSpecKeys; k += 2) {
               float x0, x1;
               unpack_f32x2(ffma2(pack_f32x2(s[k], s[k + 1]), c2, neg_mc2), x0, x1);
               pe[k] = ex2_approx(x0);
@@ -270,26 +290,27 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
         const float cy = c * (1.f / 128.f);                 // y = sat(s*cy + by) encodes x = 128*y - 120
         const float by = (neg_mc + 120.f) * (1.f / 128.f);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint32_t pk[16];
+        for (int g = 0; g < 8; ++g) {  // 16 keys per group -> 8 packed fp16x2 columns
+          uint32_t pk[8];
 #pragma unroll
-          for (int k = 0; k < 32; k += 4) {
+          for (int k = 0; k < 16; k += 4) {
+            const int e = g * 16 + k;
             float p0, p1, p2, p3;
-            if (q == 0) {
-              p0 = pe[k]; p1 = pe[k + 1]; p2 = pe[k + 2]; p3 = pe[k + 3];
+            if (e < kSpecKeys) {
+              p0 = pe[e]; p1 = pe[e + 1]; p2 = pe[e + 2]; p3 = pe[e + 3];
             } else {
               // of every 8 keys, kPolyPer8 take the FMA-pipe polynomial and the rest the MUFU
               float x0, x1, x2, x3;
               if ((k & 7) < kPolyPer8) {
-                exp2_poly_pair(pack_f32x2(ffma_sat(s[q * 32 + k + 0], cy, by), ffma_sat(s[q * 32 + k + 1], cy, by)), p0, p1);
+                exp2_poly_pair(pack_f32x2(ffma_sat(s[e + 0], cy, by), ffma_sat(s[e + 1], cy, by)), p0, p1);
               } else {
-                unpack_f32x2(ffma2(pack_f32x2(s[q * 32 + k + 0], s[q * 32 + k + 1]), c2, neg_mc2), x0, x1);
+                unpack_f32x2(ffma2(pack_f32x2(s[e + 0], s[e + 1]), c2, neg_mc2), x0, x1);
                 p0 = ex2_approx(x0); p1 = ex2_approx(x1);
               }
               if (((k + 2) & 7) < kPolyPer8) {
-                exp2_poly_pair(pack_f32x2(ffma_sat(s[q * 32 + k + 2], cy, by), ffma_sat(s[q * 32 + k + 3], cy, by)), p2, p3);
+                exp2_poly_pair(pack_f32x2(ffma_sat(s[e + 2], cy, by), ffma_sat(s[e + 3], cy, by)), p2, p3);
               } else {
-                unpack_f32x2(ffma2(pack_f32x2(s[q * 32 + k + 2], s[q * 32 + k + 3]), c2, neg_mc2), x2, x3);
+                unpack_f32x2(ffma2(pack_f32x2(s[e + 2], s[e + 3]), c2, neg_mc2), x2, x3);
                 p2 = ex2_approx(x2); p3 = ex2_approx(x3);
               }
             }
@@ -298,13 +319,13 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
             pk[k / 2 + 0] = pack_half2(p0, p1);
             pk[k / 2 + 1] = pack_half2(p2, p3);
           }
-          tmem_st_x16(t_s + q * 16, pk);  // P (fp16 pairs) overwrites columns [0,64) of its own S
-          if (q >= 2) {
+          tmem_st_x8(t_s + g * 8, pk);  // P (fp16 pairs) overwrites columns [0,64) of its own S
+          if (g == kSplitGroups - 1 || g == 7) {
             tmem_wait_st();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&p_full[i * Cfg::kPChunks + (q - 2)]);
-            if (q == 2 && (warp & 3) == 0 && lane == 0) FA_TRACE_POINT(i, j, 4);
+            if (lane == 0) mbar_arrive(&p_full[i * Cfg::kPChunks + (g == 7 ? 1 : 0)]);
+            if (g != 7 && (warp & 3) == 0 && lane == 0) FA_TRACE_POINT(i, j, 4);
           }
         }
         if ((warp & 3) == 0 && lane == 0) FA_TRACE_POINT(i, j, 5);
@@ -492,13 +513,13 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
         }
         __syncwarp();
       };
-      // O_i (+)= P_i[:, chunk c] V[chunk c, :]: chunk 0 = keys [0,96) (six 16-key MMAs), chunk 1 = [96,128)
+      // O_i (+)= P_i[:, chunk c] V[chunk c, :]: chunk 0 = the first kSplitGroups 16-key MMAs, chunk 1 = the rest
       auto issue_pv_chunk = [&](int i, int slot, int c, bool accumulate, uint64_t* done0, uint64_t* done1) {
         const uint32_t b0 = kv_addr + slot * Cfg::kTileBytes;
         const uint32_t d = tmem_base + (i == 0 ? Cfg::kColO0 : Cfg::kColO1);
         const uint32_t a = tmem_base + (i == 0 ? Cfg::kColS0 : Cfg::kColS1);
         if (elect_one()) {
-          const int ks_begin = (c == 0) ? 0 : 6, ks_end = (c == 0) ? 6 : 8;
+          const int ks_begin = (c == 0) ? 0 : kSplitGroups, ks_end = (c == 0) ? kSplitGroups : 8;
 #pragma unroll
           for (int ks = ks_begin; ks < ks_end; ++ks) {
             // V tile: rows = keys (128 B of head dim each): MN-major B operand, 16 keys = 2048 B per step
