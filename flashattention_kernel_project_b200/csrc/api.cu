@@ -247,7 +247,7 @@ int run_gemm(const void* A, const void* Bm, const float* bias, const float* resi
   p.M = M;
   p.N = N;
   p.K = K;
-  p.m_blocks = (M + GemmCfg::kBM - 1) / GemmCfg::kBM;
+  p.m_blocks = (M + 255) / 256;  // 256 x 256 output tiles, one per CTA pair
   p.n_blocks = (N + GemmCfg::kBN - 1) / GemmCfg::kBN;
   p.bias = bias;
   p.residual = residual;
@@ -255,7 +255,8 @@ int run_gemm(const void* A, const void* Bm, const float* bias, const float* resi
   p.dbg = debug_channel();
   const long long tiles = static_cast<long long>(p.m_blocks) * p.n_blocks;
   if (tiles > 0x7fffffffll) return FA_ERR_BAD_SHAPE;
-  const int grid = static_cast<int>(tiles < st->sm_count ? tiles : st->sm_count);
+  const long long pairs_max = st->sm_count / 2;  // one CTA pair (cluster of 2) per TPC, persistent
+  const int grid = 2 * static_cast<int>(tiles < pairs_max ? tiles : pairs_max);
   gemm_fused_kernel<<<grid, GemmCfg::kThreads, GemmCfg::kSmemBytes, static_cast<cudaStream_t>(stream)>>>(ma, mb, p);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   const cudaError_t e = cudaGetLastError();

@@ -1,6 +1,6 @@
-// C = ReLU(A*B + bias[col]) + residual on sm_100a: persistent CTAs, TMA A/B ring ->
-// tcgen05.mma 128x256x16 -> double-buffered fp32 accumulators in TMEM -> tcgen05.ld -> fused
-// epilogue -> global.
+// C = ReLU(A*B + bias[col]) + residual on sm_100a: persistent CTA PAIRS (cluster of 2), TMA A/B ring ->
+// tcgen05.mma.cta_group::2 256x256x16 -> double-buffered fp32 accumulators in TMEM -> tcgen05.ld ->
+// fused epilogue -> global.
 //
 // Replaces wmma_gemm_fused_kernel (GEMM/tensorcore_gemm_fused_epilogue/tensorcore_gemm_fused_epilogue.cu:53-130):
 // one warp per 16x16 C tile, WMMA fragments loaded straight from global every k-step (:80-88),
@@ -9,9 +9,20 @@
 // UMMA operand -- no host-side transposition), bias fp32 [N] / residual fp32 [M,N] nullable,
 // epilogue order bias -> ReLU -> residual (:109-126).
 //
-// CTA = 256 threads: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator,
-// warps 4-7 epilogue (warp & 3 selects the TMEM lane quadrant).  While the epilogue drains
-// accumulator `a`, the mainloop of the next tile fills accumulator `a ^ 1`.
+// Two CTAs on the two SMs of a TPC work on one 256x256 output tile.  CTA r of the pair owns rows
+// [128r, 128r+128): it loads its own 128x64 A block and HALF of the 64x256 B block (columns
+// [128r, 128r+128)) per k-step, and its TMEM holds its 128x256 half of the accumulator.  The leader
+// CTA (rank 0) issues tcgen05.mma.cta_group::2 (M = 256, N = 256): the hardware reads A from both
+// CTAs' shared memory and assembles B from the two halves, so each SM fetches 32 KB per k-block from L2
+// instead of 48 KB and reads 64 B/clk of operands from shared memory instead of 96 B/clk.
+//
+// CTA = 256 threads: warp 0 TMA producer, warp 1 MMA issuer (leader CTA only), warp 2 TMEM allocator,
+// warps 4-7 epilogue (warp & 3 selects the TMEM lane quadrant).  While the epilogues drain accumulator
+// `a`, the mainloop of the next tile fills accumulator `a ^ 1`.
+// Cross-CTA signalling: both producers' TMA loads complete_tx on the LEADER's full barrier
+// (cp.async.bulk.tensor ... cta_group::2 with the peer bit of the barrier address cleared); the leader's
+// tcgen05.commit multicasts "slot free" / "accumulator full" to both CTAs; the epilogue warps of both
+// CTAs arrive remotely on the leader's "accumulator empty" barrier.
 #pragma once
 #include "sm100_ptx.cuh"
 
@@ -19,7 +30,7 @@ namespace fa {
 
 struct GemmParams {
   int M, N, K;
-  int m_blocks, n_blocks;  // ceil(M/128), ceil(N/256)
+  int m_blocks, n_blocks;  // ceil(M/256), ceil(N/256): tiles of the CTA pair
   const float* bias;       // [N] or null
   const float* residual;   // [M,N] or null
   float* C;                // [M,N]
@@ -27,12 +38,13 @@ struct GemmParams {
 };
 
 struct GemmCfg {
-  static constexpr int kBM = 128, kBN = 256, kBK = 64;
-  static constexpr int kStages = 4;
+  static constexpr int kBM = 128;   // rows per CTA (256 per pair)
+  static constexpr int kBN = 256, kBK = 64;
+  static constexpr int kStages = 6;
   static constexpr int kABytes = kBM * kBK * 2;            // 16 KB: one 128B-swizzled box
   static constexpr int kBBoxBytes = 64 * 128;              // 64 k-rows x 128 B (64 n columns)
-  static constexpr int kBBytes = (kBN / 64) * kBBoxBytes;  // 32 KB
-  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBBytes = (kBN / 2 / 64) * kBBoxBytes;  // this CTA's half of B: 16 KB
+  static constexpr int kStageBytes = kABytes + kBBytes;    // 32 KB per CTA
   static constexpr int kOffBar = kStages * kStageBytes;
   static constexpr int kNumBars = 2 * kStages + 4;
   static constexpr int kOffTmem = kOffBar + kNumBars * 8;
@@ -44,6 +56,57 @@ struct GemmCfg {
 
 enum : uint32_t { SITE_G_EMPTY = 0x21, SITE_G_FULL, SITE_G_TEMPTY, SITE_G_TFULL };
 
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address -> rank 0 of the pair
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose completion bytes are credited to the barrier at the same offset in the LEADER CTA
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                                uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0),
+      "r"(c1), "l"(hint)
+      : "memory");
+}
+__device__ __forceinline__ void umma_ss_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once all prior tcgen05 ops of this thread completed) on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_2sm_mc(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2sm() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
 __device__ __forceinline__ void gemm_tile_coords(int tile, const GemmParams& p, int& mb, int& nb) {
   const int band_tiles = GemmCfg::kGroupN * p.m_blocks;
   const int band = tile / band_tiles;
@@ -54,20 +117,23 @@ __device__ __forceinline__ void gemm_tile_coords(int tile, const GemmParams& p, 
   nb = n_first + rem % band_w;
 }
 
-__global__ void __launch_bounds__(256, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
 gemm_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                   const GemmParams p) {
   using Cfg = GemmCfg;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBar);
-  uint64_t* const full = bars;                        // [kStages] TMA -> MMA
-  uint64_t* const empty = bars + Cfg::kStages;        // [kStages] MMA -> TMA
-  uint64_t* const tfull = empty + Cfg::kStages;       // [2] MMA -> epilogue
-  uint64_t* const tempty = tfull + 2;                 // [2] epilogue -> MMA
+  uint64_t* const full = bars;                        // [kStages] TMA (both CTAs) -> MMA; used in the leader only
+  uint64_t* const empty = bars + Cfg::kStages;        // [kStages] MMA -> TMA, multicast to both CTAs
+  uint64_t* const tfull = empty + Cfg::kStages;       // [2] MMA -> epilogue, multicast to both CTAs
+  uint64_t* const tempty = tfull + 2;                 // [2] epilogues of both CTAs -> MMA; used in the leader only
   uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(smem + Cfg::kOffTmem);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();            // 0 = leader
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
   const DebugChannel dbg = p.dbg;
   const int num_tiles = p.m_blocks * p.n_blocks;
   const int num_kb = (p.K + Cfg::kBK - 1) / Cfg::kBK;
@@ -75,12 +141,12 @@ gemm_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   if (warp == 1 && lane == 0) {
     if ((smem_u32(smem) & 1023u) != 0u) wait_timeout_trap(dbg, 0xA12u, 0, smem_u32(smem));
     for (int s = 0; s < Cfg::kStages; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&full[s], 1);   // the leader's producer arrives once and expects the bytes of both CTAs
+      mbar_init(&empty[s], 1);  // one multicast commit from the leader's MMA warp
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 128);
+      mbar_init(&tempty[a], 8);  // 4 epilogue warps x 2 CTAs
     }
     fence_mbar_init();
   }
@@ -89,46 +155,44 @@ gemm_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     prefetch_tensormap(&mapB);
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
+    tmem_alloc_2sm(tmem_slot, 512);
+    tmem_relinquish_2sm();
   }
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();  // barrier inits of both CTAs visible before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------- TMA producer -----------------------------------
+    // ------------------------------- TMA producer (both CTAs) -------------------------
     // whole warp walks the schedule; the lane chosen by elect.sync issues (see fa_fwd.cuh)
-    {
-      int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        int mb, nb;
-        gemm_tile_coords(tile, p, mb, nb);
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % Cfg::kStages;
-          const int par = (it / Cfg::kStages) & 1;
-          mbar_wait(&empty[s], par ^ 1, dbg, SITE_G_EMPTY, it);
-          uint8_t* const a_dst = smem + s * Cfg::kStageBytes;
-          uint8_t* const b_dst = a_dst + Cfg::kABytes;
-          if (elect_one()) {
-            mbar_arrive_expect_tx(&full[s], Cfg::kStageBytes);
-            tma_load_2d(a_dst, &mapA, &full[s], kb * Cfg::kBK, mb * Cfg::kBM, kEvictNormal);
+    int it = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      int mb, nb;
+      gemm_tile_coords(tile, p, mb, nb);
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int s = it % Cfg::kStages;
+        const int par = (it / Cfg::kStages) & 1;
+        mbar_wait(&empty[s], par ^ 1, dbg, SITE_G_EMPTY, it);
+        uint8_t* const a_dst = smem + s * Cfg::kStageBytes;
+        uint8_t* const b_dst = a_dst + Cfg::kABytes;
+        if (elect_one()) {
+          if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * Cfg::kStageBytes);
+          tma_load_2d_2sm(a_dst, &mapA, &full[s], kb * Cfg::kBK, mb * 256 + static_cast<int>(rank) * Cfg::kBM, kEvictNormal);
 #pragma unroll
-            for (int b = 0; b < Cfg::kBN / 64; ++b)
-              tma_load_2d(b_dst + b * Cfg::kBBoxBytes, &mapB, &full[s], nb * Cfg::kBN + b * 64, kb * Cfg::kBK,
-                          kEvictNormal);
-          }
-          __syncwarp();
+          for (int b = 0; b < Cfg::kBN / 2 / 64; ++b)
+            tma_load_2d_2sm(b_dst + b * Cfg::kBBoxBytes, &mapB, &full[s],
+                            nb * Cfg::kBN + static_cast<int>(rank) * (Cfg::kBN / 2) + b * 64, kb * Cfg::kBK, kEvictNormal);
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    // -------------------------------- MMA issuer -------------------------------------
-    {
-      constexpr uint32_t idesc = umma_idesc_f16(Cfg::kBM, Cfg::kBN, 0, 1);
+    // -------------------------------- MMA issuer (leader CTA) -------------------------
+    if (rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(256, Cfg::kBN, 0, 1);
       int it = 0, local = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      for (int tile = pair; tile < num_tiles; tile += num_pairs, ++local) {
         const int acc = local & 1;
         const int acc_par = (local >> 1) & 1;
         mbar_wait(&tempty[acc], acc_par ^ 1, dbg, SITE_G_TEMPTY, local);
@@ -144,30 +208,30 @@ gemm_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           if (elect_one()) {
 #pragma unroll
             for (int ks = 0; ks < Cfg::kBK / 16; ++ks) {
-              umma_ss(d, umma_desc_sw128(a0 + ks * 32, 16, 1024),
-                      umma_desc_sw128(b0 + ks * 2048, Cfg::kBBoxBytes, 1024), idesc, (kb | ks) ? 1u : 0u);
+              umma_ss_2sm(d, umma_desc_sw128(a0 + ks * 32, 16, 1024),
+                          umma_desc_sw128(b0 + ks * 2048, Cfg::kBBoxBytes, 1024), idesc, (kb | ks) ? 1u : 0u);
             }
-            umma_commit(&empty[s]);
-            if (kb == num_kb - 1) umma_commit(&tfull[acc]);
+            umma_commit_2sm_mc(&empty[s]);
+            if (kb == num_kb - 1) umma_commit_2sm_mc(&tfull[acc]);
           }
           __syncwarp();
         }
       }
     }
   } else if (warp >= 4) {
-    // --------------------------------- epilogue --------------------------------------
+    // --------------------------------- epilogue (both CTAs) ---------------------------
     const int wq = warp & 3;
     const int row_in_tile = wq * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(wq * 32) << 16;
     int local = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++local) {
       int mb, nb;
       gemm_tile_coords(tile, p, mb, nb);
       const int acc = local & 1;
       const int acc_par = (local >> 1) & 1;
       mbar_wait(&tfull[acc], acc_par, dbg, SITE_G_TFULL, local);
       tc_fence_after();
-      const int grow = mb * Cfg::kBM + row_in_tile;
+      const int grow = mb * 256 + static_cast<int>(rank) * Cfg::kBM + row_in_tile;
       const bool row_ok = grow < p.M;
       const size_t row_off = static_cast<size_t>(grow) * p.N;
 #pragma unroll 1
@@ -198,14 +262,15 @@ gemm_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         }
       }
       tc_fence_before();
-      mbar_arrive(&tempty[acc]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tempty[acc]);
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();  // no CTA of the pair may exit (or free TMEM) while the other still signals it
   tc_fence_after();
-  if (warp == 2) tmem_dealloc(tmem_base, 512);
+  if (warp == 2) tmem_dealloc_2sm(tmem_base, 512);
 }
 
 }  // namespace fa
