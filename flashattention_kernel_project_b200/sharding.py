@@ -30,10 +30,21 @@ def ring_schedule(world_size, rank):
     return [(rank - s) % world_size for s in range(world_size)]
 
 
+def new_ring_group(ranks=None):
+    """NCCL group for the K/V exchange with a HIGH-PRIORITY internal stream.  The attention kernel occupies
+    every SM (one 227 KB CTA each), so NCCL's send/recv kernel only gets scheduled while attention runs if its
+    stream outranks the compute stream: measured on 2 x B200, a 512 MiB exchange issued next to a 15 ms
+    attention launch takes 1.5 ms with the high-priority stream and 14-19 ms (i.e. after the kernel) without."""
+    opts = dist.ProcessGroupNCCL.Options()
+    opts.is_high_priority_stream = True
+    return dist.new_group(ranks=ranks, backend="nccl", pg_options=opts)
+
+
 def ring_attention(q, k, v, scale, group=None, step_fn=None, comm_stream=None):
     """Context-parallel attention over the ranks of `group`.
 
     q, k, v: this rank's [B, H, N/P, D] fp16 shards.  Returns this rank's [B, H, N/P, D] output.
+    On GPUs pass a group made by `new_ring_group()` so the exchange overlaps the attention kernel.
     K/V for step s+1 are received into the alternate buffer while step s computes (double
     buffering; on GPUs the exchange runs on `comm_stream`).  `step_fn` defaults to the CUDA entry
     point `fa_forward_partial`; the gloo CPU tests inject a torch fp32 implementation of the same

@@ -39,7 +39,7 @@ def _worker(rank, world, port, mode, q, k, v, scale, out_path):
             n = N // world
             sl = slice(rank * n, (rank + 1) * n)
             out = fa.ring_attention(q[:, :, sl].contiguous().cuda(), k[:, :, sl].contiguous().cuda(),
-                                    v[:, :, sl].contiguous().cuda(), scale)
+                                    v[:, :, sl].contiguous().cuda(), scale, group=fa.new_ring_group())
             torch.cuda.synchronize()
             gathered = [torch.empty_like(out) for _ in range(world)]
             dist.all_gather(gathered, out)  # test-only
