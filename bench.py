@@ -305,7 +305,7 @@ def reference_gpu_kernels(torch, dev):
     the fused WMMA GEMM at 8192^3, the naive softmax at 16384 x 4096.  Never on the product path."""
     try:
         from tests.oracle_lib import RefGpu, ref_available
-        if not all(ref_available(n) for n in ("wmma_v5", "gemm_fused", "softmax_naive")):
+        if not all(ref_available(n) for n in ("wmma_v5", "gemm_fused", "softmax_naive", "v12i", "v7_5")):
             return {"unavailable": "oracle/_ref not built"}
         ref = RefGpu()
     except Exception as e:  # noqa: BLE001
@@ -317,6 +317,19 @@ def reference_gpu_kernels(torch, dev):
         torch.cuda.synchronize()
         return time_loop(torch, fn, iters) / iters
 
+    # the two comparators BASELINE.json names, at their native shapes (B=1024, L=128, D=16), next to fa_forward_cross
+    import flashattention_kernel_project_b200 as fa
+    q16 = (torch.rand((1024, 16, 16), device=dev) * 2 - 1).half()
+    k16, v16 = ((torch.rand((1024, 128, 16), device=dev) * 2 - 1).half() for _ in range(2))
+    o16 = torch.zeros((1024, 16, 16), device=dev)
+    out["v12i_native_B1024_M16_L128_D16"] = {
+        "reference_us": timeit(lambda: ref.v12i_kernel(q16, k16, v16, o16, 0.25), 200) * 1e3,
+        "ours_us": timeit(lambda: fa.fa_forward_cross(q16[None], k16[None], v16[None], 0.25, out=o16[None]), 200) * 1e3}
+    q1, o1 = q16[:, 0].contiguous(), torch.zeros((1024, 16), device=dev)
+    out["v7_5_native_B1024_S128_D16_single_query"] = {
+        "reference_us": timeit(lambda: ref.v7_5_kernel(q1, k16, v16, o1), 200) * 1e3,
+        "ours_us": timeit(lambda: fa.fa_forward_cross(q1.view(1, 1024, 1, 16), k16[None], v16[None], 0.25,
+                                                      out=o1.view(1, 1024, 1, 16)), 200) * 1e3}
     B, H, N, D = 4, 16, 1024, 64
     q, k, v = ((torch.rand((B, H, N, D), device=dev) * 2 - 1).half() for _ in range(3))
     o = torch.zeros((B, H, N, D), device=dev)

@@ -17,6 +17,7 @@ SIGNATURES = {
     "fa_strerror": (ctypes.c_char_p, [c_int]),
     "fa_forward": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_float, c_void_p]),
     "fa_forward_f32out": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_float, c_void_p]),
+    "fa_forward_cross": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_float, c_void_p]),
     "fa_forward_partial": (c_int, [c_void_p] * 6 + [c_int] * 5 + [c_float, c_int, c_int, c_void_p, c_void_p]),
     "gemm_fused_epilogue": (c_int, [c_void_p] * 5 + [c_int] * 3 + [c_void_p]),
     "softmax_rows": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),

@@ -13,6 +13,7 @@
 
 #include "../../include/fa_b200.h"
 #include "fa_fwd.cuh"
+#include "fa_small.cuh"
 #include "gemm_fused.cuh"
 #include "softmax_rows.cuh"
 
@@ -360,6 +361,30 @@ int fa_forward_partial(const void* Q, const void* K, const void* V, float* O_acc
                        int Nq, int Nkv, int D, float scale, int is_first, int is_last, void* O_final, void* stream) {
   FaCall c{Q, K, V, is_last ? O_final : nullptr, O_acc, m, l, B, H, Nq, Nkv, D, scale, FA_MODE_STATE,
            is_first ? 1 : 0, is_last ? 1 : 0};
+  return run_fa(c, stream);
+}
+
+int fa_forward_cross(const void* Q, const void* K, const void* V, float* O, int B, int H, int Nq, int Nkv, int D,
+                     float scale, void* stream) {
+  if (D == 16) {
+    if (B <= 0 || H <= 0 || Nq <= 0 || Nkv <= 0) return FA_ERR_BAD_SHAPE;
+    if (!(scale == scale) || std::isinf(scale)) return FA_ERR_BAD_ARGUMENT;
+    if (Q == nullptr || K == nullptr || V == nullptr || O == nullptr) return FA_ERR_NULL_POINTER;
+    if (!aligned16(Q) || !aligned16(K) || !aligned16(V) || !aligned16(O)) return FA_ERR_MISALIGNED;
+    DeviceState* st = nullptr;
+    int rc = current_device_state(&st);
+    if (rc != FA_OK) return rc;
+    const long long rows = static_cast<long long>(B) * H * Nq;
+    const long long ctas = (rows + 7) / 8;
+    if (ctas > 0x7fffffffll) return FA_ERR_BAD_SHAPE;
+    fa_fwd_d16_kernel<<<static_cast<unsigned>(ctas), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __half*>(Q), static_cast<const __half*>(K), static_cast<const __half*>(V), O, rows, Nq, Nkv,
+        scale * 1.4426950408889634f);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? FA_OK : static_cast<int>(e);
+  }
+  FaCall c{Q, K, V, nullptr, O, nullptr, nullptr, B, H, Nq, Nkv, D, scale, FA_MODE_F32, 1, 1};
   return run_fa(c, stream);
 }
 

@@ -78,6 +78,25 @@ def fa_forward_f32out(q, k, v, scale=None, out=None, stream=None):
     return out
 
 
+def fa_forward_cross(q, k, v, scale=None, out=None, stream=None):
+    """Attention with Nq != Nkv and fp32 output; D in {16, 64, 128}.  D = 16 is the native shape of the
+    reference's v12i (Q [B,M,16], K,V [B,L,16]) and v7_5 (one query per batch element) programs."""
+    B, H, Nq, D = _bhnd(q)
+    Bk, Hk, Nkv, Dk = _bhnd(k)
+    if (Bk, Hk, Dk) != (B, H, D) or tuple(v.shape) != tuple(k.shape):
+        raise ValueError("K, V must be [B, H, Nkv, D] matching Q's B, H, D")
+    if scale is None:
+        scale = 1.0 / float(D) ** 0.5
+    if out is None:
+        out = torch.empty((B, H, Nq, D), dtype=torch.float32, device=q.device)
+    lib = load_library()
+    with torch.cuda.device(q.device):
+        check(lib.fa_forward_cross(_dev_ptr(q, torch.float16, "Q"), _dev_ptr(k, torch.float16, "K"),
+                                   _dev_ptr(v, torch.float16, "V"), _dev_ptr(out, torch.float32, "O"),
+                                   B, H, Nq, Nkv, D, float(scale), _stream_ptr(stream)), "fa_forward_cross")
+    return out
+
+
 def fa_forward_partial(q, k, v, o_acc, m, l, scale, is_first, is_last, o_final=None, stream=None):
     """One ring step: fold attention of Q against one K/V shard into the carried (O_acc, m, l)."""
     B, H, Nq, D = _bhnd(q)

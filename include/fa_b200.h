@@ -28,7 +28,7 @@ extern "C" {
 
 #define FA_OK 0
 #define FA_ERR_BAD_SHAPE (-1)      /* non-positive extent, or product overflows the index range   */
-#define FA_ERR_BAD_HEAD_DIM (-2)   /* D not in {64, 128}                                          */
+#define FA_ERR_BAD_HEAD_DIM (-2)   /* D not in {64, 128} (fa_forward_cross: {16, 64, 128})        */
 #define FA_ERR_MISALIGNED (-3)     /* pointer not 16-byte aligned / row pitch not a multiple of 16 B */
 #define FA_ERR_NULL_POINTER (-4)
 #define FA_ERR_NO_DEVICE (-5)      /* current device is not compute capability 10.x               */
@@ -56,6 +56,19 @@ int fa_forward(const void* Q, const void* K, const void* V, void* O, int B, int 
 /* Same, fp32 output as the reference kernels write it (`float* O`, flashattn_forward_wmma.cu:49-58). */
 int fa_forward_f32out(const void* Q, const void* K, const void* V, float* O, int B, int H, int N, int D,
                       float scale, void* stream);
+
+/*
+ * Attention with a query count different from the key count (decode / cross shapes), fp32 output:
+ *   Q fp16 [B,H,Nq,D], K, V fp16 [B,H,Nkv,D], O fp32 [B,H,Nq,D];  D in {16, 64, 128}.
+ * D = 16 covers the comparators BASELINE.json names at their native shapes:
+ *   flashattn_2warp_nosmemW_online_softmax<16,16,4,32>(Q, K, V, O, seq_len, m_total, scale)
+ *     (flashattn_warp_spc/flashattn_streaming_16x32_2warp_softmax_v12i.cu:60-70; B=1024, M=16, L=128)
+ *   flashattn_streaming_16x16_kernel_mw_v7_5(Q, K, V, O, S, inv_sqrt_d)
+ *     (flashattn_warp_spc_v2/flashattn_streaming_16x16_mw_v7_5_spinless_cpasync2stage.cu:84-91; one query per b: Nq = 1)
+ * and the D = 16 streaming family (flashattn_warp_spc/flashattn_streaming_16x16_mw_v10.cu:104-112, with K as [B,L,16]).
+ */
+int fa_forward_cross(const void* Q, const void* K, const void* V, float* O, int B, int H, int Nq, int Nkv, int D,
+                     float scale, void* stream);
 
 /*
  * One step of a context-parallel (ring) attention: attends Q [B,H,Nq,D] to ONE K/V shard

@@ -28,6 +28,11 @@ def main():
     o = r.v12i_cpu_reference(q, k, v, 0.25)
     np.savez_compressed(os.path.join(HERE, "attn_v12i_native.npz"), q=q.view(np.uint16), k=k.view(np.uint16),
                         v=v.view(np.uint16), o=o, scale=np.float32(0.25))
+    # v7_5's native shape, reduced batch: one query per batch element, S=128, D=16, mt19937(0), scale 1/4
+    # (flashattn_warp_spc_v2/..v7_5..cu:250-283 oracle, :297-303 generator)
+    q, k, v = r.v7_5_fill(0, 32, 128)
+    np.savez_compressed(os.path.join(HERE, "attn_v7_5_native.npz"), q=q.view(np.uint16), k=k.view(np.uint16),
+                        v=v.view(np.uint16), o=r.v7_5_cpu_ref(q, k, v), scale=np.float32(0.25))
     # ragged D=128 case (N=200: one full and one partial 128-key tile), 2 (b,h) pairs
     q, k, v = r.v12i_fill_uniform(7, (2, 200, 128), (2, 200, 128), (2, 200, 128))
     sc = np.float32(1.0 / np.sqrt(128.0))

@@ -162,6 +162,9 @@ class RefCpu:
         self.v12i.ref_v12i_rel_l2.argtypes = [_f32p, _f32p, c_size_t]
         self.v12i.ref_v12i_rel_l2.restype = c_double
         self.v12i.ref_v12i_fill_uniform.argtypes = [ctypes.c_uint, _u16p, c_size_t, _u16p, c_size_t, _u16p, c_size_t]
+        self.v75 = RefLib("v7_5").L
+        self.v75.ref_v7_5_cpu_ref.argtypes = [_u16p, _u16p, _u16p, _f32p, c_int, c_int]
+        self.v75.ref_v7_5_fill.argtypes = [ctypes.c_uint, _u16p, c_size_t, _u16p, c_size_t, _u16p, c_size_t]
         self.fa542 = RefLib("fa542").L
         self.fa542.ref_fa542_cpu_ref.argtypes = [_f32p] * 4 + [c_int] * 3
         self.sb = RefLib("softmax_block").L
@@ -186,6 +189,18 @@ class RefCpu:
         a = np.ascontiguousarray(a, dtype=np.float32).ravel()
         b = np.ascontiguousarray(b, dtype=np.float32).ravel()
         return float(self.v12i.ref_v12i_rel_l2(a, b, a.size))
+
+    def v7_5_cpu_ref(self, q, k, v):
+        """q [B, 16], k, v [B, S, 16] fp16 -> fp32 [B, 16] (single query per batch element, scale 1/4)."""
+        B, S = q.shape[0], k.shape[1]
+        out = np.empty((B, 16), dtype=np.float32)
+        self.v75.ref_v7_5_cpu_ref(_as_u16(q), _as_u16(k), _as_u16(v), out, B, S)
+        return out
+
+    def v7_5_fill(self, seed, B, S):
+        q, k, v = np.empty((B, 16), np.uint16), np.empty((B, S, 16), np.uint16), np.empty((B, S, 16), np.uint16)
+        self.v75.ref_v7_5_fill(seed, q, q.size, k, k.size, v, v.size)
+        return q.view(np.float16), k.view(np.float16), v.view(np.float16)
 
     def fa542_cpu_ref(self, q, k, v):
         BH, N, D = q.shape
@@ -226,6 +241,8 @@ class RefGpu:
         self.v4.ref_wmma_v4_launch.argtypes = [vp, vp, vp, vp, c_int, c_int, c_int, c_float, vp]
         self.v12i = RefLib("v12i").L
         self.v12i.ref_v12i_launch.argtypes = [vp, vp, vp, vp, c_int, c_int, c_int, c_float, vp]
+        self.v75 = RefLib("v7_5").L
+        self.v75.ref_v7_5_launch.argtypes = [vp, vp, vp, vp, c_int, c_int, c_float, vp]
         self.gemm = RefLib("gemm_fused").L
         self.gemm.ref_gemm_fused_launch.argtypes = [vp, vp, vp, vp, vp, c_int, c_int, c_int, vp]
         self.softmax = RefLib("softmax_naive").L
@@ -250,6 +267,11 @@ class RefGpu:
         B, M, L = q.shape[0], q.shape[1], k.shape[1]
         self._chk(self.v12i.ref_v12i_launch(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, M, L,
                                             float(scale), stream), "v12i")
+
+    def v7_5_kernel(self, q, k, v, out, stream=0):
+        B, S = q.shape[0], k.shape[1]
+        self._chk(self.v75.ref_v7_5_launch(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, S, 0.25, stream),
+                  "v7_5")
 
     def gemm_fused(self, a, b, bias, residual, out, stream=0):
         M, K = a.shape

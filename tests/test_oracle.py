@@ -24,6 +24,15 @@ def test_attention_f16_matches_reference_golden_bit_exact(oracle, golden, name):
     assert np.array_equal(oracle.attention_f16(g["q"], g["k"], g["v"], float(g["scale"]), nthreads=1), g["o"])
 
 
+def test_single_query_golden_from_v7_5(oracle, golden):
+    """v7_5's cpu_ref_attention (one query per batch element, -1e30 sentinel) is the same arithmetic as
+    v12i's cpu_reference with M_TOTAL = 1: the restatement reproduces its output bit for bit."""
+    g = golden("attn_v7_5_native.npz")
+    q = g["q"].reshape(-1, 1, 16)
+    out = oracle.attention_f16(q, g["k"], g["v"], float(g["scale"]))
+    assert np.array_equal(out.reshape(-1, 16), g["o"])
+
+
 def test_attention_rows_sampling_equals_full(oracle, golden):
     g = golden("attn_ragged_d128.npz")
     rows = np.array([0, 1, 127, 128, 199, 200, 333, 399], dtype=np.int64)
