@@ -1,0 +1,62 @@
+"""CPU check that the shipped library really is Blackwell-native: the SASS of libfa_b200.so must contain the
+tcgen05 / TMA / TMEM instructions the design claims (mnemonics per /opt/skills/guides/B200_PROFILING.md) and no
+legacy tensor path (HMMA = mma.sync / wmma)."""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+import flashattention_kernel_project_b200 as fa
+
+
+@pytest.fixture(scope="module")
+def sass():
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    if not os.path.exists(fa.lib_path()):
+        import __graft_entry__ as g
+        g.build_cuda()
+    out = subprocess.run([cuobjdump, "-sass", fa.lib_path()], capture_output=True, text=True, check=True).stdout
+    funcs, cur = {}, None
+    for line in out.splitlines():
+        if "Function :" in line:
+            cur = line.split("Function :")[1].strip()
+            funcs[cur] = []
+        elif cur is not None:
+            funcs[cur].append(line)
+    return {k: "\n".join(v) for k, v in funcs.items()}
+
+
+def _one(sass, needle):
+    hits = [k for k in sass if needle in k]
+    assert hits, f"no kernel matching {needle}"
+    return [sass[k] for k in hits]
+
+
+def test_attention_kernel_uses_tcgen05_tmem_and_tma(sass):
+    for body in _one(sass, "fa_fwd_kernel"):
+        assert "UTCHMMA" in body          # tcgen05.mma
+        assert "LDTM" in body and "STTM" in body  # tcgen05.ld / tcgen05.st (S out of TMEM, P back into TMEM)
+        assert "UTMALDG" in body and "UTMASTG" in body  # TMA tile loads and the TMA store of O
+        assert "SYNCS" in body            # mbarrier phase waits
+        assert "USETMAXREG" in body       # setmaxnreg register redistribution between roles
+        assert "MUFU.EX2" in body         # exp2-domain softmax
+        assert "HMMA" not in body.replace("UTCHMMA", "")  # no mma.sync / wmma path
+        assert "BRA.U.ANY" not in body    # no per-thread serialisation loops around uniform-datapath instructions
+
+
+def test_gemm_kernel_uses_cta_pairs(sass):
+    for body in _one(sass, "gemm_fused_kernel"):
+        assert "UTCHMMA.2CTA" in body     # tcgen05.mma.cta_group::2
+        assert "UTMALDG.2D.2CTA" in body  # 2-SM TMA loads signalling the leader's barrier
+        assert "UTCBAR.2CTA.MULTICAST" in body  # multicast tcgen05.commit
+        assert "LDTM" in body
+        assert "HMMA" not in body.replace("UTCHMMA", "")
+
+
+def test_softmax_kernels_are_plain_bandwidth_kernels(sass):
+    for body in _one(sass, "softmax_rows_reg_kernel"):
+        assert "LDG.E.128" in body or "LDG.E.EF.128" in body or ".128" in body  # 128-bit global accesses
+        assert "UTCHMMA" not in body and "HMMA" not in body
