@@ -240,6 +240,16 @@ int run_gemm(const void* A, const void* Bm, const float* bias, const float* resi
   const uint32_t bb[2] = {64, 64};
   if ((rc = make_map(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, A, 2, da, ba)) != FA_OK) return rc;
   if ((rc = make_map(&mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, Bm, 2, db, bb)) != FA_OK) return rc;
+  // epilogue blocks: 128 rows x 32 fp32 columns of C / residual
+  CUtensorMap mr, mc;
+  const uint64_t dc[2] = {static_cast<uint64_t>(N), static_cast<uint64_t>(M)};
+  const uint32_t bc[2] = {GemmCfg::kEpiCols, GemmCfg::kBM};
+  if ((rc = make_map(&mc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, C, 2, dc, bc)) != FA_OK) return rc;
+  if (residual != nullptr) {
+    if ((rc = make_map(&mr, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, residual, 2, dc, bc)) != FA_OK) return rc;
+  } else {
+    mr = mc;  // never dereferenced without a residual
+  }
   {
     std::lock_guard<std::mutex> lock(g_mutex);
     if ((rc = ensure_smem_attr(&st->attr_gemm, gemm_fused_kernel, GemmCfg::kSmemBytes)) != FA_OK) return rc;
@@ -258,7 +268,7 @@ int run_gemm(const void* A, const void* Bm, const float* bias, const float* resi
   if (tiles > 0x7fffffffll) return FA_ERR_BAD_SHAPE;
   const long long pairs_max = st->sm_count / 2;  // one CTA pair (cluster of 2) per TPC, persistent
   const int grid = 2 * static_cast<int>(tiles < pairs_max ? tiles : pairs_max);
-  gemm_fused_kernel<<<grid, GemmCfg::kThreads, GemmCfg::kSmemBytes, static_cast<cudaStream_t>(stream)>>>(ma, mb, p);
+  gemm_fused_kernel<<<grid, GemmCfg::kThreads, GemmCfg::kSmemBytes, static_cast<cudaStream_t>(stream)>>>(ma, mb, mr, mc, p);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   const cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? FA_OK : static_cast<int>(e);

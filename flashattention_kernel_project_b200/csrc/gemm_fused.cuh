@@ -17,7 +17,8 @@
 // instead of 48 KB and reads 64 B/clk of operands from shared memory instead of 96 B/clk.
 //
 // CTA = 256 threads: warp 0 TMA producer, warp 1 MMA issuer (leader CTA only), warp 2 TMEM allocator,
-// warps 4-7 epilogue (warp & 3 selects the TMEM lane quadrant).  While the epilogues drain accumulator
+// warps 4-7 epilogue (warp & 3 selects the TMEM lane quadrant): accumulator -> registers -> bias/ReLU -> combined
+// in shared memory with a residual block fetched by TMA -> TMA store.  While the epilogues drain accumulator
 // `a`, the mainloop of the next tile fills accumulator `a ^ 1`.
 // Cross-CTA signalling: both producers' TMA loads complete_tx on the LEADER's full barrier
 // (cp.async.bulk.tensor ... cta_group::2 with the peer bit of the barrier address cleared); the leader's
@@ -40,21 +41,28 @@ struct GemmParams {
 struct GemmCfg {
   static constexpr int kBM = 128;   // rows per CTA (256 per pair)
   static constexpr int kBN = 256, kBK = 64;
-  static constexpr int kStages = 6;
+  static constexpr int kStages = 5;
   static constexpr int kABytes = kBM * kBK * 2;            // 16 KB: one 128B-swizzled box
   static constexpr int kBBoxBytes = 64 * 128;              // 64 k-rows x 128 B (64 n columns)
   static constexpr int kBBytes = (kBN / 2 / 64) * kBBoxBytes;  // this CTA's half of B: 16 KB
   static constexpr int kStageBytes = kABytes + kBBytes;    // 32 KB per CTA
+  // epilogue ring: kEpiBufs buffers of 128 rows x 32 fp32 columns (one 128B-swizzled TMA box each).  A buffer
+  // receives a residual block by TMA, is updated in place with the accumulator, and leaves by TMA store.
+  static constexpr int kEpiCols = 32;
+  static constexpr int kEpiBufs = 4;
+  static constexpr int kEpiBufBytes = kBM * kEpiCols * 4;  // 16 KB
+  static constexpr int kChunksPerTile = kBN / kEpiCols;    // 8
   static constexpr int kOffBar = kStages * kStageBytes;
-  static constexpr int kNumBars = 2 * kStages + 4;
+  static constexpr int kNumBars = 2 * kStages + 4 + kEpiBufs;
   static constexpr int kOffTmem = kOffBar + kNumBars * 8;
-  static constexpr int kSmemBytes = kOffTmem + 16;
+  static constexpr int kOffEpi = (kOffTmem + 16 + 1023) / 1024 * 1024;
+  static constexpr int kSmemBytes = kOffEpi + kEpiBufs * kEpiBufBytes;
   static constexpr int kThreads = 256;
   static constexpr int kGroupN = 8;  // rasterisation: bands of 8 n-blocks, m fastest inside a band
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
 };
 
-enum : uint32_t { SITE_G_EMPTY = 0x21, SITE_G_FULL, SITE_G_TEMPTY, SITE_G_TFULL };
+enum : uint32_t { SITE_G_EMPTY = 0x21, SITE_G_FULL, SITE_G_TEMPTY, SITE_G_TFULL, SITE_G_RFULL };
 
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address -> rank 0 of the pair
 
@@ -119,6 +127,7 @@ __device__ __forceinline__ void gemm_tile_coords(int tile, const GemmParams& p, 
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
 gemm_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                  const __grid_constant__ CUtensorMap mapR, const __grid_constant__ CUtensorMap mapC,
                   const GemmParams p) {
   using Cfg = GemmCfg;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -127,6 +136,7 @@ gemm_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   uint64_t* const empty = bars + Cfg::kStages;        // [kStages] MMA -> TMA, multicast to both CTAs
   uint64_t* const tfull = empty + Cfg::kStages;       // [2] MMA -> epilogue, multicast to both CTAs
   uint64_t* const tempty = tfull + 2;                 // [2] epilogues of both CTAs -> MMA; used in the leader only
+  uint64_t* const rfull = tempty + 2;                 // [kEpiBufs] residual block landed (CTA-local)
   uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(smem + Cfg::kOffTmem);
 
   const int warp = threadIdx.x >> 5;
@@ -148,11 +158,14 @@ gemm_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       mbar_init(&tfull[a], 1);
       mbar_init(&tempty[a], 8);  // 4 epilogue warps x 2 CTAs
     }
+    for (int b = 0; b < Cfg::kEpiBufs; ++b) mbar_init(&rfull[b], 1);
     fence_mbar_init();
   }
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&mapA);
     prefetch_tensormap(&mapB);
+    prefetch_tensormap(&mapR);
+    prefetch_tensormap(&mapC);
   }
   if (warp == 2) {
     tmem_alloc_2sm(tmem_slot, 512);
@@ -220,10 +233,31 @@ gemm_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     }
   } else if (warp >= 4) {
     // --------------------------------- epilogue (both CTAs) ---------------------------
+    // A lane owns one accumulator row (tcgen05.ld 32x32b), which is the worst shape for global memory, and four
+    // warps cannot keep enough loads in flight to cover DRAM latency.  So TMA moves the data: the residual block of
+    // chunk g+3 is in flight while chunk g is combined IN PLACE in shared memory (128B swizzle: the 8 lanes of a
+    // quarter-warp hit 8 different 16-byte columns, no bank conflicts) and chunk g-1 drains through a TMA store.
     const int wq = warp & 3;
     const int row_in_tile = wq * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(wq * 32) << 16;
-    int local = 0;
+    const bool chief = threadIdx.x == 128;
+    const bool has_res = p.residual != nullptr;
+    uint8_t* const ebuf = smem + Cfg::kOffEpi;
+    const int my_tiles = (num_tiles - pair + num_pairs - 1) / num_pairs;
+    const int total_chunks = my_tiles * Cfg::kChunksPerTile;
+    const int row0 = static_cast<int>(rank) * Cfg::kBM;
+    auto load_residual = [&](int g) {
+      int mb, nb;
+      gemm_tile_coords(pair + (g / Cfg::kChunksPerTile) * num_pairs, p, mb, nb);
+      const int b = g % Cfg::kEpiBufs;
+      mbar_arrive_expect_tx(&rfull[b], Cfg::kEpiBufBytes);
+      tma_load_2d(ebuf + b * Cfg::kEpiBufBytes, &mapR, &rfull[b], nb * Cfg::kBN + (g % Cfg::kChunksPerTile) * Cfg::kEpiCols,
+                  mb * 256 + row0, kEvictFirst);
+    };
+    if (chief && has_res) {
+      for (int g = 0; g < Cfg::kEpiBufs - 1 && g < total_chunks; ++g) load_residual(g);
+    }
+    int local = 0, g = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++local) {
       int mb, nb;
       gemm_tile_coords(tile, p, mb, nb);
@@ -231,40 +265,48 @@ gemm_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       const int acc_par = (local >> 1) & 1;
       mbar_wait(&tfull[acc], acc_par, dbg, SITE_G_TFULL, local);
       tc_fence_after();
-      const int grow = mb * 256 + static_cast<int>(rank) * Cfg::kBM + row_in_tile;
-      const bool row_ok = grow < p.M;
-      const size_t row_off = static_cast<size_t>(grow) * p.N;
 #pragma unroll 1
-      for (int cc = 0; cc < Cfg::kBN / 32; ++cc) {
+      for (int cc = 0; cc < Cfg::kChunksPerTile; ++cc, ++g) {
+        const int b = g % Cfg::kEpiBufs;
         uint32_t r[32];
-        tmem_ld_x32(tmem_base + lane_base + acc * Cfg::kBN + cc * 32, r);
+        tmem_ld_x32(tmem_base + lane_base + acc * Cfg::kBN + cc * Cfg::kEpiCols, r);
+        if (has_res) mbar_wait(&rfull[b], (g / Cfg::kEpiBufs) & 1, dbg, SITE_G_RFULL, g);
         tmem_wait_ld();
-        const int col0 = nb * Cfg::kBN + cc * 32;
-        if (row_ok) {
+        if (cc == Cfg::kChunksPerTile - 1) {  // accumulator drained into registers: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(&tempty[acc]);
+        }
+        uint8_t* const rowp = ebuf + b * Cfg::kEpiBufBytes + row_in_tile * 128;
+        const int col0 = nb * Cfg::kBN + cc * Cfg::kEpiCols;
 #pragma unroll
-          for (int k = 0; k < 32; k += 4) {
-            const int col = col0 + k;
-            if (col < p.N) {  // N % 8 == 0, so a 4-wide group is entirely inside or outside
-              float4 v = make_float4(__uint_as_float(r[k]), __uint_as_float(r[k + 1]),
-                                     __uint_as_float(r[k + 2]), __uint_as_float(r[k + 3]));
-              if (p.bias != nullptr) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-              }
-              v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-              if (p.residual != nullptr) {
-                const float4 q = __ldcs(reinterpret_cast<const float4*>(p.residual + row_off + col));
-                v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
-              }
-              __stcs(reinterpret_cast<float4*>(p.C + row_off + col), v);
-            }
+        for (int q = 0; q < 8; ++q) {
+          float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
+                                 __uint_as_float(r[4 * q + 3]));
+          const int col = col0 + q * 4;
+          if (p.bias != nullptr && col < p.N) {  // N % 8 == 0, so a 4-wide group is entirely inside or outside
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+            v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
           }
+          v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+          float4* const slot = reinterpret_cast<float4*>(rowp + ((q ^ (row_in_tile & 7)) << 4));
+          if (has_res) {
+            const float4 q4 = *slot;
+            v.x += q4.x; v.y += q4.y; v.z += q4.z; v.w += q4.w;
+          }
+          *slot = v;
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (chief) {
+          tma_store_2d(&mapC, ebuf + b * Cfg::kEpiBufBytes, col0, mb * 256 + row0);  // rows >= M, cols >= N are clipped
+          tma_store_commit();
+          tma_store_wait_read<1>();  // the store of chunk g-1 has left its buffer, which chunk g+3 reuses
+          if (has_res && g + Cfg::kEpiBufs - 1 < total_chunks) load_residual(g + Cfg::kEpiBufs - 1);
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_leader(&tempty[acc]);
     }
+    if (chief) tma_store_wait_all<0>();
   }
 
   tc_fence_before();
