@@ -68,7 +68,7 @@ struct DeviceState {
   bool probed = false;
   bool is_sm100 = false;
   int sm_count = 0;
-  bool attr_fa64 = false, attr_fa128 = false, attr_gemm = false;
+  bool attr_fa64 = false, attr_fa128 = false, attr_gemm = false, attr_gemm_t = false;
   // scratch for the *_host entry points
   void* scratch[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   size_t scratch_bytes[6] = {0, 0, 0, 0, 0, 0};
@@ -223,55 +223,86 @@ int run_fa(const FaCall& c, void* stream) {
 }
 
 // ---- GEMM ---------------------------------------------------------------------------------
-int run_gemm(const void* A, const void* Bm, const float* bias, const float* residual, float* C, int M, int N, int K,
-             void* stream) {
-  if (M <= 0 || N <= 0 || K <= 0) return FA_ERR_BAD_SHAPE;
-  if (A == nullptr || Bm == nullptr || C == nullptr) return FA_ERR_NULL_POINTER;
+// C[z] = act(alpha * A[z] * op(B[z]) + bias) + residual[z] for z in [0, batch)
+struct GemmCall {
+  const void* A;
+  const void* Bm;
+  const float* bias;
+  const float* residual;
+  float* C;
+  int batch, M, N, K;
+  bool trans_b, relu;
+  float alpha;
+};
+
+int run_gemm(const GemmCall& c, void* stream) {
+  const int M = c.M, N = c.N, K = c.K;
+  if (M <= 0 || N <= 0 || K <= 0 || c.batch <= 0) return FA_ERR_BAD_SHAPE;
+  if (c.A == nullptr || c.Bm == nullptr || c.C == nullptr) return FA_ERR_NULL_POINTER;
   if ((N & 7) != 0 || (K & 7) != 0) return FA_ERR_MISALIGNED;
-  if (!aligned16(A) || !aligned16(Bm) || !aligned16(C) || !aligned16(bias) || !aligned16(residual))
+  if (!aligned16(c.A) || !aligned16(c.Bm) || !aligned16(c.C) || !aligned16(c.bias) || !aligned16(c.residual))
     return FA_ERR_MISALIGNED;
   DeviceState* st = nullptr;
   int rc = current_device_state(&st);
   if (rc != FA_OK) return rc;
-  CUtensorMap ma, mb;
-  const uint64_t da[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
-  const uint32_t ba[2] = {64, 128};
-  const uint64_t db[2] = {static_cast<uint64_t>(N), static_cast<uint64_t>(K)};
-  const uint32_t bb[2] = {64, 64};
-  if ((rc = make_map(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, A, 2, da, ba)) != FA_OK) return rc;
-  if ((rc = make_map(&mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, Bm, 2, db, bb)) != FA_OK) return rc;
+  const uint64_t Z = static_cast<uint64_t>(c.batch);
+  CUtensorMap ma, mb, mr, mc;
+  const uint64_t da[3] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M), Z};
+  const uint32_t ba[3] = {64, 128, 1};
+  if ((rc = make_map(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, c.A, 3, da, ba)) != FA_OK) return rc;
+  if (c.trans_b) {  // [N,K] rows: the same K-major boxes as A
+    const uint64_t db[3] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N), Z};
+    if ((rc = make_map(&mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, c.Bm, 3, db, ba)) != FA_OK) return rc;
+  } else {
+    const uint64_t db[3] = {static_cast<uint64_t>(N), static_cast<uint64_t>(K), Z};
+    const uint32_t bb[3] = {64, 64, 1};
+    if ((rc = make_map(&mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, c.Bm, 3, db, bb)) != FA_OK) return rc;
+  }
   // epilogue blocks: 128 rows x 32 fp32 columns of C / residual
-  CUtensorMap mr, mc;
-  const uint64_t dc[2] = {static_cast<uint64_t>(N), static_cast<uint64_t>(M)};
-  const uint32_t bc[2] = {GemmCfg::kEpiCols, GemmCfg::kBM};
-  if ((rc = make_map(&mc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, C, 2, dc, bc)) != FA_OK) return rc;
-  if (residual != nullptr) {
-    if ((rc = make_map(&mr, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, residual, 2, dc, bc)) != FA_OK) return rc;
+  const uint64_t dc[3] = {static_cast<uint64_t>(N), static_cast<uint64_t>(M), Z};
+  const uint32_t bc[3] = {GemmCfg::kEpiCols, GemmCfg::kBM, 1};
+  if ((rc = make_map(&mc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, c.C, 3, dc, bc)) != FA_OK) return rc;
+  if (c.residual != nullptr) {
+    if ((rc = make_map(&mr, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, c.residual, 3, dc, bc)) != FA_OK) return rc;
   } else {
     mr = mc;  // never dereferenced without a residual
   }
   {
     std::lock_guard<std::mutex> lock(g_mutex);
-    if ((rc = ensure_smem_attr(&st->attr_gemm, gemm_fused_kernel, GemmCfg::kSmemBytes)) != FA_OK) return rc;
+    if ((rc = ensure_smem_attr(&st->attr_gemm, gemm_fused_kernel<false>, GemmCfg::kSmemBytes)) != FA_OK) return rc;
+    if ((rc = ensure_smem_attr(&st->attr_gemm_t, gemm_fused_kernel<true>, GemmCfg::kSmemBytes)) != FA_OK) return rc;
   }
   GemmParams p;
   p.M = M;
   p.N = N;
   p.K = K;
+  p.batch = c.batch;
   p.m_blocks = (M + 255) / 256;  // 256 x 256 output tiles, one per CTA pair
   p.n_blocks = (N + GemmCfg::kBN - 1) / GemmCfg::kBN;
-  p.bias = bias;
-  p.residual = residual;
-  p.C = C;
+  p.alpha = c.alpha;
+  p.relu = c.relu ? 1 : 0;
+  p.bias = c.bias;
+  p.residual = c.residual;
+  p.C = c.C;
   p.dbg = debug_channel();
-  const long long tiles = static_cast<long long>(p.m_blocks) * p.n_blocks;
+  const long long tiles = static_cast<long long>(p.m_blocks) * p.n_blocks * c.batch;
   if (tiles > 0x7fffffffll) return FA_ERR_BAD_SHAPE;
   const long long pairs_max = st->sm_count / 2;  // one CTA pair (cluster of 2) per TPC, persistent
   const int grid = 2 * static_cast<int>(tiles < pairs_max ? tiles : pairs_max);
-  gemm_fused_kernel<<<grid, GemmCfg::kThreads, GemmCfg::kSmemBytes, static_cast<cudaStream_t>(stream)>>>(ma, mb, mr, mc, p);
+  const cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (c.trans_b)
+    gemm_fused_kernel<true><<<grid, GemmCfg::kThreads, GemmCfg::kSmemBytes, s>>>(ma, mb, mr, mc, p);
+  else
+    gemm_fused_kernel<false><<<grid, GemmCfg::kThreads, GemmCfg::kSmemBytes, s>>>(ma, mb, mr, mc, p);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   const cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? FA_OK : static_cast<int>(e);
+}
+
+int run_gemm(const void* A, const void* Bm, const float* bias, const float* residual, float* C, int M, int N, int K,
+             void* stream) {
+  const GemmCall c{A, Bm, bias, residual, C, 1, M, N, K, false, true, 1.0f};
+  return run_gemm(c, stream);
 }
 
 // ---- softmax ------------------------------------------------------------------------------
@@ -401,6 +432,12 @@ int fa_forward_cross(const void* Q, const void* K, const void* V, float* O, int 
 int gemm_fused_epilogue(const void* A, const void* Bm, const float* bias, const float* residual, float* C, int M,
                         int N, int K, void* stream) {
   return run_gemm(A, Bm, bias, residual, C, M, N, K, stream);
+}
+
+int gemm_batched(const void* A, const void* Bm, float* C, int batch, int M, int N, int K, int trans_b, float alpha,
+                 void* stream) {
+  const GemmCall c{A, Bm, nullptr, nullptr, C, batch, M, N, K, trans_b != 0, false, alpha};
+  return run_gemm(c, stream);
 }
 
 int softmax_rows(const float* X, float* P, int rows, int N, void* stream) { return run_softmax(X, P, rows, N, stream); }

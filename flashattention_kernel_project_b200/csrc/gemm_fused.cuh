@@ -30,8 +30,10 @@
 namespace fa {
 
 struct GemmParams {
-  int M, N, K;
-  int m_blocks, n_blocks;  // ceil(M/256), ceil(N/256): tiles of the CTA pair
+  int M, N, K, batch;
+  int m_blocks, n_blocks;  // ceil(M/256), ceil(N/256): tiles of the CTA pair, per batch entry
+  float alpha;             // C = act(alpha * A*op(B) + bias) + residual
+  int relu;                // 1: ReLU between bias and residual (the fused-epilogue contract), 0: identity
   const float* bias;       // [N] or null
   const float* residual;   // [M,N] or null
   float* C;                // [M,N]
@@ -75,13 +77,13 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 // TMA load whose completion bytes are credited to the barrier at the same offset in the LEADER CTA
-__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
-                                                uint64_t hint) {
+__device__ __forceinline__ void tma_load_3d_2sm(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                                int c2, uint64_t hint) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-      " [%0], [%1, {%3, %4}], [%2], %5;"
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;"
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0),
-      "r"(c1), "l"(hint)
+      "r"(c1), "r"(c2), "l"(hint)
       : "memory");
 }
 __device__ __forceinline__ void umma_ss_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
@@ -115,7 +117,10 @@ __device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols)
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
-__device__ __forceinline__ void gemm_tile_coords(int tile, const GemmParams& p, int& mb, int& nb) {
+__device__ __forceinline__ void gemm_tile_coords(int tile, const GemmParams& p, int& bz, int& mb, int& nb) {
+  const int per_batch = p.m_blocks * p.n_blocks;
+  bz = tile / per_batch;
+  tile -= bz * per_batch;
   const int band_tiles = GemmCfg::kGroupN * p.m_blocks;
   const int band = tile / band_tiles;
   const int rem = tile - band * band_tiles;
@@ -125,6 +130,9 @@ __device__ __forceinline__ void gemm_tile_coords(int tile, const GemmParams& p, 
   nb = n_first + rem % band_w;
 }
 
+// kTransB = false: B is [K,N] row-major (an MN-major operand, two 64-column boxes per CTA and k-block);
+// kTransB = true:  B is [N,K] row-major, C = A * B^T (a K-major operand like A, one 128-row box).
+template <bool kTransB>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
 gemm_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                   const __grid_constant__ CUtensorMap mapR, const __grid_constant__ CUtensorMap mapC,
@@ -145,7 +153,7 @@ gemm_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   const int pair = blockIdx.x >> 1;
   const int num_pairs = gridDim.x >> 1;
   const DebugChannel dbg = p.dbg;
-  const int num_tiles = p.m_blocks * p.n_blocks;
+  const int num_tiles = p.batch * p.m_blocks * p.n_blocks;
   const int num_kb = (p.K + Cfg::kBK - 1) / Cfg::kBK;
 
   if (warp == 1 && lane == 0) {
@@ -181,8 +189,8 @@ gemm_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     // whole warp walks the schedule; the lane chosen by elect.sync issues (see fa_fwd.cuh)
     int it = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-      int mb, nb;
-      gemm_tile_coords(tile, p, mb, nb);
+      int bz, mb, nb;
+      gemm_tile_coords(tile, p, bz, mb, nb);
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
         const int s = it % Cfg::kStages;
         const int par = (it / Cfg::kStages) & 1;
@@ -191,11 +199,16 @@ gemm_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         uint8_t* const b_dst = a_dst + Cfg::kABytes;
         if (elect_one()) {
           if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * Cfg::kStageBytes);
-          tma_load_2d_2sm(a_dst, &mapA, &full[s], kb * Cfg::kBK, mb * 256 + static_cast<int>(rank) * Cfg::kBM, kEvictNormal);
+          tma_load_3d_2sm(a_dst, &mapA, &full[s], kb * Cfg::kBK, mb * 256 + static_cast<int>(rank) * Cfg::kBM, bz,
+                          kEvictNormal);
+          const int n0 = nb * Cfg::kBN + static_cast<int>(rank) * (Cfg::kBN / 2);  // this CTA's half of the B block
+          if constexpr (kTransB) {
+            tma_load_3d_2sm(b_dst, &mapB, &full[s], kb * Cfg::kBK, n0, bz, kEvictNormal);
+          } else {
 #pragma unroll
-          for (int b = 0; b < Cfg::kBN / 2 / 64; ++b)
-            tma_load_2d_2sm(b_dst + b * Cfg::kBBoxBytes, &mapB, &full[s],
-                            nb * Cfg::kBN + static_cast<int>(rank) * (Cfg::kBN / 2) + b * 64, kb * Cfg::kBK, kEvictNormal);
+            for (int b = 0; b < Cfg::kBN / 2 / 64; ++b)
+              tma_load_3d_2sm(b_dst + b * Cfg::kBBoxBytes, &mapB, &full[s], n0 + b * 64, kb * Cfg::kBK, bz, kEvictNormal);
+          }
         }
         __syncwarp();
       }
@@ -203,7 +216,7 @@ gemm_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   } else if (warp == 1) {
     // -------------------------------- MMA issuer (leader CTA) -------------------------
     if (rank == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(256, Cfg::kBN, 0, 1);
+      constexpr uint32_t idesc = umma_idesc_f16(256, Cfg::kBN, 0, kTransB ? 0 : 1);
       int it = 0, local = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs, ++local) {
         const int acc = local & 1;
@@ -221,8 +234,9 @@ gemm_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           if (elect_one()) {
 #pragma unroll
             for (int ks = 0; ks < Cfg::kBK / 16; ++ks) {
-              umma_ss_2sm(d, umma_desc_sw128(a0 + ks * 32, 16, 1024),
-                          umma_desc_sw128(b0 + ks * 2048, Cfg::kBBoxBytes, 1024), idesc, (kb | ks) ? 1u : 0u);
+              const uint64_t db = kTransB ? umma_desc_sw128(b0 + ks * 32, 16, 1024)
+                                          : umma_desc_sw128(b0 + ks * 2048, Cfg::kBBoxBytes, 1024);
+              umma_ss_2sm(d, umma_desc_sw128(a0 + ks * 32, 16, 1024), db, idesc, (kb | ks) ? 1u : 0u);
             }
             umma_commit_2sm_mc(&empty[s]);
             if (kb == num_kb - 1) umma_commit_2sm_mc(&tfull[acc]);
@@ -247,20 +261,20 @@ gemm_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     const int total_chunks = my_tiles * Cfg::kChunksPerTile;
     const int row0 = static_cast<int>(rank) * Cfg::kBM;
     auto load_residual = [&](int g) {
-      int mb, nb;
-      gemm_tile_coords(pair + (g / Cfg::kChunksPerTile) * num_pairs, p, mb, nb);
+      int bz, mb, nb;
+      gemm_tile_coords(pair + (g / Cfg::kChunksPerTile) * num_pairs, p, bz, mb, nb);
       const int b = g % Cfg::kEpiBufs;
       mbar_arrive_expect_tx(&rfull[b], Cfg::kEpiBufBytes);
-      tma_load_2d(ebuf + b * Cfg::kEpiBufBytes, &mapR, &rfull[b], nb * Cfg::kBN + (g % Cfg::kChunksPerTile) * Cfg::kEpiCols,
-                  mb * 256 + row0, kEvictFirst);
+      tma_load_3d(ebuf + b * Cfg::kEpiBufBytes, &mapR, &rfull[b], nb * Cfg::kBN + (g % Cfg::kChunksPerTile) * Cfg::kEpiCols,
+                  mb * 256 + row0, bz, kEvictFirst);
     };
     if (chief && has_res) {
       for (int g = 0; g < Cfg::kEpiBufs - 1 && g < total_chunks; ++g) load_residual(g);
     }
     int local = 0, g = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++local) {
-      int mb, nb;
-      gemm_tile_coords(tile, p, mb, nb);
+      int bz, mb, nb;
+      gemm_tile_coords(tile, p, bz, mb, nb);
       const int acc = local & 1;
       const int acc_par = (local >> 1) & 1;
       mbar_wait(&tfull[acc], acc_par, dbg, SITE_G_TFULL, local);
@@ -281,14 +295,16 @@ gemm_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         const int col0 = nb * Cfg::kBN + cc * Cfg::kEpiCols;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
-                                 __uint_as_float(r[4 * q + 3]));
+          float4 v = make_float4(__uint_as_float(r[4 * q]) * p.alpha, __uint_as_float(r[4 * q + 1]) * p.alpha,
+                                 __uint_as_float(r[4 * q + 2]) * p.alpha, __uint_as_float(r[4 * q + 3]) * p.alpha);
           const int col = col0 + q * 4;
           if (p.bias != nullptr && col < p.N) {  // N % 8 == 0, so a 4-wide group is entirely inside or outside
             const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
             v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
           }
-          v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+          if (p.relu) {
+            v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+          }
           float4* const slot = reinterpret_cast<float4*>(rowp + ((q ^ (row_in_tile & 7)) << 4));
           if (has_res) {
             const float4 q4 = *slot;
@@ -299,7 +315,7 @@ gemm_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         fence_proxy_async_smem();
         named_bar_sync(1, 128);
         if (chief) {
-          tma_store_2d(&mapC, ebuf + b * Cfg::kEpiBufBytes, col0, mb * 256 + row0);  // rows >= M, cols >= N are clipped
+          tma_store_3d(&mapC, ebuf + b * Cfg::kEpiBufBytes, col0, mb * 256 + row0, bz);  // rows >= M, cols >= N are clipped
           tma_store_commit();
           tma_store_wait_read<1>();  // the store of chunk g-1 has left its buffer, which chunk g+3 reuses
           if (has_res && g + Cfg::kEpiBufs - 1 < total_chunks) load_residual(g + Cfg::kEpiBufs - 1);

@@ -140,6 +140,31 @@ def gemm_fused_epilogue(a, b, bias=None, residual=None, out=None, stream=None):
     return out
 
 
+def gemm_batched(a, b, trans_b=False, alpha=1.0, out=None, stream=None):
+    """C[z] = alpha * A[z] @ op(B[z]); A fp16 [batch,M,K]; B fp16 [batch,K,N], or [batch,N,K] with trans_b; C fp32.
+
+    trans_b=False, alpha=1: wmma_batched_gemm_kernel (gemm_4_9_tensorcore_batched.cu:42-46);
+    trans_b=True, alpha=scale: QK_wmma_kernel (qk_wmma_5_1_2.cu:32-38)."""
+    _require_cuda(a, "A")
+    _require_cuda(b, "B")
+    if a.dim() != 3 or b.dim() != 3 or a.shape[0] != b.shape[0]:
+        raise ValueError("A must be [batch, M, K] and B [batch, K, N] (or [batch, N, K] with trans_b)")
+    batch, M, K = (int(v) for v in a.shape)
+    N = int(b.shape[1] if trans_b else b.shape[2])
+    if int(b.shape[2] if trans_b else b.shape[1]) != K:
+        raise ValueError("inner extents of A and B differ")
+    if out is None:
+        out = torch.empty((batch, M, N), dtype=torch.float32, device=a.device)
+    elif tuple(out.shape) != (batch, M, N):
+        raise ValueError("C must be [batch, M, N]")
+    lib = load_library()
+    with torch.cuda.device(a.device):
+        check(lib.gemm_batched(_dev_ptr(a, torch.float16, "A"), _dev_ptr(b, torch.float16, "B"),
+                               _dev_ptr(out, torch.float32, "C"), batch, M, N, K, 1 if trans_b else 0, float(alpha),
+                               _stream_ptr(stream)), "gemm_batched")
+    return out
+
+
 def softmax_rows(x, out=None, stream=None):
     """Row softmax of an fp32 [rows, N] matrix (softmax_naive_baseline.cu:56-61)."""
     _require_cuda(x, "X")

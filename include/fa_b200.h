@@ -97,6 +97,20 @@ int gemm_fused_epilogue(const void* A, const void* Bm, const float* bias, const 
                         int M, int N, int K, void* stream);
 
 /*
+ * Batched plain GEMM with a scale: C[z] = alpha * A[z] * op(B[z]) for z in [0, batch), no bias / activation.
+ *   A fp16 [batch,M,K]; Bm fp16 [batch,K,N] if trans_b == 0, fp16 [batch,N,K] if trans_b != 0 (C = alpha*A*B^T);
+ *   C fp32 [batch,M,N]; all row-major and densely packed; K % 8 == 0 and N % 8 == 0.
+ * Replaces: wmma_batched_gemm_kernel(A, B, C, batch, M, N, K)            (trans_b = 0, alpha = 1)
+ *             (GEMM/gemm_tensorcore_batched/gemm_4_9_tensorcore_batched.cu:42-46)
+ *           QK_wmma_kernel(Q, K, Scores, BH, N, D, scale)                 (trans_b = 1: A = Q, Bm = K, M = N = seq, K = D, alpha = scale)
+ *             (GEMM/QK Tensor Core/qk_wmma_5_1_2.cu:32-38)
+ *           wmma_gemm_tensorcore_kernel(A, B, C, M, N, K)                 (batch = 1; the QK^T and PV stages of
+ *             FlashAttention/flashattn_forward_memory_bound/flashattn_stage_latency_breakdown.cu:58-65)
+ */
+int gemm_batched(const void* A, const void* Bm, float* C, int batch, int M, int N, int K, int trans_b, float alpha,
+                 void* stream);
+
+/*
  * Row softmax, P[r, :] = softmax(X[r, :]) with max subtraction; X, P fp32 [rows, N]; in place allowed.
  * Replaces: softmax_naive_baseline_kernel(scores, probs, num_rows, N)
  *   (Softmax micro kernel/softmax_naive_baseline/softmax_naive_baseline.cu:56-61).

@@ -334,6 +334,63 @@ void fa_oracle_gemm_fused_f16(const uint16_t* A, const uint16_t* B, const float*
 }
 
 /* ---------------------------------------------------------------------------------------
+ * Batched plain GEMM, C[b] = A[b]*B[b], fp32 accumulate, k ascending -- restates
+ * cpu_batched_gemm_ref (GEMM/gemm_tensorcore_batched/gemm_4_9_tensorcore_batched.cu:94-121).
+ * A [batch,M,K], B [batch,K,N], C [batch,M,N], fp32.  The reference harness hands it the UNROUNDED
+ * fp32 operands (:145) while its kernel gets fp16 copies (:150-151); the parity tests here feed
+ * it the half-rounded values widened to float, i.e. exactly what the GPU sees.
+ * ------------------------------------------------------------------------------------- */
+void fa_oracle_gemm_batched(const float* A, const float* B, float* C, int batch, int M, int N, int K, int nthreads) {
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#else
+  (void)nthreads;
+#endif
+#pragma omp parallel for collapse(2) schedule(dynamic, 8)
+  for (int b = 0; b < batch; ++b) {
+    for (int i = 0; i < M; ++i) {
+      const float* Ab = A + (size_t)b * M * K;
+      const float* Bb = B + (size_t)b * K * N;
+      float* Cb = C + (size_t)b * M * N;
+      for (int j = 0; j < N; ++j) {
+        float acc = 0.0f;
+        for (int k = 0; k < K; ++k) acc += Ab[(size_t)i * K + k] * Bb[(size_t)k * N + j];
+        Cb[(size_t)i * N + j] = acc;
+      }
+    }
+  }
+}
+
+/* ---------------------------------------------------------------------------------------
+ * Scores[b,i,j] = scale * sum_k Q[b,i,k] K[b,j,k], double accumulate, one final rounding --
+ * restates qk_cpu_ref (GEMM/QK Tensor Core/qk_wmma_5_1_2.cu:101-122).  Q [BH,N,D], Kmat [BH,Nk,D];
+ * the reference has Nk == N, the extra extent costs nothing here.
+ * ------------------------------------------------------------------------------------- */
+void fa_oracle_qk_scores(const float* Q, const float* Kmat, float* S, int BH, int N, int Nk, int D, float scale,
+                         int nthreads) {
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#else
+  (void)nthreads;
+#endif
+#pragma omp parallel for collapse(2) schedule(dynamic, 8)
+  for (int b = 0; b < BH; ++b) {
+    for (int i = 0; i < N; ++i) {
+      for (int j = 0; j < Nk; ++j) {
+        double acc = 0.0;
+        for (int k = 0; k < D; ++k) {
+          const float qv = Q[((size_t)b * N + i) * D + k];
+          const float kv = Kmat[((size_t)b * Nk + j) * D + k];
+          acc += (double)qv * kv;
+        }
+        acc *= scale;
+        S[((size_t)b * N + i) * Nk + j] = (float)acc;
+      }
+    }
+  }
+}
+
+/* ---------------------------------------------------------------------------------------
  * Error metrics, adopted verbatim: rel_l2 = sqrt(sum (a-b)^2 / (sum b^2 + 1e-30))
  * (flashattn_streaming_16x32_2warp_softmax_v12i.cu:288-296); max_abs = max |a-b| in double
  * (tensorcore_gemm_fused_epilogue.cu:247-254).

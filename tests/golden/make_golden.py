@@ -49,6 +49,15 @@ def main():
     a, b, bias, res = r.gemm_fused_fill(42, 48, 64, 80)
     np.savez_compressed(os.path.join(HERE, "gemm_fused.npz"), a=a, b=b, bias=bias, residual=res,
                         c=r.gemm_fused_cpu(a, b, bias, res))
+    # batched plain GEMM (gemm_4_9_tensorcore_batched.cu:94-121) and scaled QK^T (qk_wmma_5_1_2.cu:101-122) on
+    # half-rounded operands widened to fp32, as both harnesses feed their CPU reference
+    rng2 = np.random.default_rng(49)
+    ab = rng2.uniform(-1, 1, (3, 32, 48)).astype(np.float16).astype(np.float32)
+    bb = rng2.uniform(-1, 1, (3, 48, 40)).astype(np.float16).astype(np.float32)
+    np.savez_compressed(os.path.join(HERE, "gemm_batched.npz"), a=ab, b=bb, c=r.gemm_batched_cpu(ab, bb))
+    qq = rng2.uniform(-1, 1, (2, 48, 64)).astype(np.float16).astype(np.float32)
+    kk = rng2.uniform(-1, 1, (2, 48, 64)).astype(np.float16).astype(np.float32)
+    np.savez_compressed(os.path.join(HERE, "qk_scores.npz"), q=qq, k=kk, s=r.qk_cpu(qq, kk, 0.125), scale=np.float32(0.125))
     # row softmax through flashattn_ref with K = V = I, scale = 1 (its softmax step, :242-252)
     n = 48
     x = (rng.standard_normal((1, n, n)) * 3).astype(np.float32)

@@ -45,6 +45,8 @@ class Oracle:
         L.fa_oracle_softmax_rows.argtypes = [_f32p, _f32p, c_ll, c_int, c_int]
         L.fa_oracle_gemm_fused.argtypes = [_f32p, _f32p, ctypes.c_void_p, ctypes.c_void_p, _f32p] + [c_int] * 6
         L.fa_oracle_gemm_fused_f16.argtypes = [_u16p, _u16p, ctypes.c_void_p, ctypes.c_void_p, _f32p] + [c_int] * 6
+        L.fa_oracle_gemm_batched.argtypes = [_f32p, _f32p, _f32p] + [c_int] * 5
+        L.fa_oracle_qk_scores.argtypes = [_f32p, _f32p, _f32p] + [c_int] * 4 + [c_float, c_int]
         L.fa_oracle_rel_l2.argtypes = [_f32p, _f32p, c_size_t]
         L.fa_oracle_rel_l2.restype = c_double
         L.fa_oracle_max_abs.argtypes = [_f32p, _f32p, c_size_t]
@@ -115,6 +117,26 @@ class Oracle:
                                         row_begin, row_end, nthreads)
         return out
 
+    def gemm_batched(self, a, b, nthreads=0):
+        """fp32 [batch,M,K] x [batch,K,N] -> [batch,M,N], fp32 accumulate (cpu_batched_gemm_ref)."""
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        b = np.ascontiguousarray(b, dtype=np.float32)
+        batch, M, K = a.shape
+        N = b.shape[2]
+        out = np.empty((batch, M, N), dtype=np.float32)
+        self.L.fa_oracle_gemm_batched(a, b, out, batch, M, N, K, nthreads)
+        return out
+
+    def qk_scores(self, q, k, scale, nthreads=0):
+        """fp32 q [BH,N,D], k [BH,Nk,D] -> scale * q k^T [BH,N,Nk], double accumulate (qk_cpu_ref)."""
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        k = np.ascontiguousarray(k, dtype=np.float32)
+        BH, N, D = q.shape
+        Nk = k.shape[1]
+        out = np.empty((BH, N, Nk), dtype=np.float32)
+        self.L.fa_oracle_qk_scores(q, k, out, BH, N, Nk, D, float(scale), nthreads)
+        return out
+
     def rel_l2(self, a, b):
         a = np.ascontiguousarray(a, dtype=np.float32).ravel()
         b = np.ascontiguousarray(b, dtype=np.float32).ravel()
@@ -172,6 +194,13 @@ class RefCpu:
         self.gemm = RefLib("gemm_fused").L
         self.gemm.ref_gemm_fused_cpu.argtypes = [_f32p] * 5 + [c_int] * 3
         self.gemm.ref_gemm_fused_fill.argtypes = [ctypes.c_uint] + [_f32p, c_size_t] * 4
+        # added after the first fixtures were cut: absent in an older prebuilt oracle/_ref
+        self.bgemm = RefLib("gemm_batched").L if ref_available("gemm_batched") else None
+        if self.bgemm is not None:
+            self.bgemm.ref_gemm_batched_cpu.argtypes = [_f32p] * 3 + [c_int] * 4
+        self.qk = RefLib("qk_wmma").L if ref_available("qk_wmma") else None
+        if self.qk is not None:
+            self.qk.ref_qk_cpu.argtypes = [_f32p] * 3 + [c_int] * 3 + [c_float]
 
     def v12i_cpu_reference(self, q, k, v, scale):
         B, M, KD = q.shape
@@ -223,6 +252,21 @@ class RefCpu:
                                      M, N, K)
         return out
 
+    def gemm_batched_cpu(self, a, b):
+        batch, M, K = a.shape
+        N = b.shape[2]
+        out = np.empty((batch, M, N), dtype=np.float32)
+        self.bgemm.ref_gemm_batched_cpu(np.ascontiguousarray(a, dtype=np.float32), np.ascontiguousarray(b, dtype=np.float32),
+                                        out, batch, M, N, K)
+        return out
+
+    def qk_cpu(self, q, k, scale):
+        BH, N, D = q.shape
+        out = np.empty((BH, N, N), dtype=np.float32)
+        self.qk.ref_qk_cpu(np.ascontiguousarray(q, dtype=np.float32), np.ascontiguousarray(k, dtype=np.float32), out,
+                           BH, N, D, float(scale))
+        return out
+
     def gemm_fused_fill(self, seed, M, N, K):
         a, b = np.empty((M, K), np.float32), np.empty((K, N), np.float32)
         bias, res = np.empty((N,), np.float32), np.empty((M, N), np.float32)
@@ -247,6 +291,10 @@ class RefGpu:
         self.gemm.ref_gemm_fused_launch.argtypes = [vp, vp, vp, vp, vp, c_int, c_int, c_int, vp]
         self.softmax = RefLib("softmax_naive").L
         self.softmax.ref_softmax_naive_launch.argtypes = [vp, vp, c_int, c_int, vp]
+        self.bgemm = RefLib("gemm_batched").L
+        self.bgemm.ref_gemm_batched_launch.argtypes = [vp, vp, vp, c_int, c_int, c_int, c_int, vp]
+        self.qk = RefLib("qk_wmma").L
+        self.qk.ref_qk_launch.argtypes = [vp, vp, vp, c_int, c_int, c_int, c_float, vp]
 
     @staticmethod
     def _chk(rc, what):
@@ -283,3 +331,14 @@ class RefGpu:
     def softmax_naive(self, x, out, stream=0):
         self._chk(self.softmax.ref_softmax_naive_launch(x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], stream),
                   "softmax_naive")
+
+    def gemm_batched(self, a, b, out, stream=0):
+        batch, M, K = a.shape
+        N = b.shape[2]
+        self._chk(self.bgemm.ref_gemm_batched_launch(a.data_ptr(), b.data_ptr(), out.data_ptr(), batch, M, N, K, stream),
+                  "gemm_batched")
+
+    def qk_wmma(self, q, k, out, scale, stream=0):
+        BH, N, D = q.shape
+        self._chk(self.qk.ref_qk_launch(q.data_ptr(), k.data_ptr(), out.data_ptr(), BH, N, D, float(scale), stream),
+                  "qk_wmma")

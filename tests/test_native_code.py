@@ -50,7 +50,8 @@ def test_attention_kernel_uses_tcgen05_tmem_and_tma(sass):
 def test_gemm_kernel_uses_cta_pairs(sass):
     for body in _one(sass, "gemm_fused_kernel"):
         assert "UTCHMMA.2CTA" in body     # tcgen05.mma.cta_group::2
-        assert "UTMALDG.2D.2CTA" in body  # 2-SM TMA loads signalling the leader's barrier
+        assert "UTMALDG.3D.2CTA" in body  # 2-SM TMA loads (batch is the third coordinate) signalling the leader's barrier
+        assert "UTMASTG.3D" in body       # the epilogue leaves through TMA stores
         assert "UTCBAR.2CTA.MULTICAST" in body  # multicast tcgen05.commit
         assert "LDTM" in body
         assert "HMMA" not in body.replace("UTCHMMA", "")

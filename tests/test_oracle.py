@@ -78,6 +78,21 @@ def test_gemm_fused_matches_golden_and_nullable_operands(oracle, golden):
     assert np.array_equal(f16, f32[8:24])
 
 
+def test_gemm_batched_and_qk_scores_match_golden(oracle, golden):
+    g = golden("gemm_batched.npz")
+    c = oracle.gemm_batched(g["a"], g["b"])
+    assert np.array_equal(c, g["c"])
+    assert np.allclose(c, np.einsum("bmk,bkn->bmn", g["a"].astype(np.float64), g["b"].astype(np.float64)), atol=1e-4)
+    # one batch entry of the batched GEMM == the fused GEMM's contraction before its epilogue on non-negative results
+    g = golden("qk_scores.npz")
+    s = oracle.qk_scores(g["q"], g["k"], float(g["scale"]))
+    assert np.array_equal(s, g["s"])
+    assert np.allclose(s, 0.125 * np.einsum("bik,bjk->bij", g["q"].astype(np.float64), g["k"].astype(np.float64)), atol=1e-6)
+    # Nk != N is accepted by the restatement (the reference fixes Nk = N)
+    s2 = oracle.qk_scores(g["q"], g["k"][:, :17], float(g["scale"]))
+    assert np.array_equal(s2, s[:, :, :17])
+
+
 def test_softmax_rows_matches_golden(oracle, golden):
     g = golden("softmax_rows.npz")
     p = oracle.softmax_rows(g["x"])
@@ -126,3 +141,8 @@ def test_oracle_bit_exact_against_compiled_reference(oracle):
     assert np.array_equal(r.softmax_block_flashattn_ref(qf, kf, vf, 0.7), oracle.attention_f32(qf, kf, vf, 0.7))
     a, b, bias, res = r.gemm_fused_fill(43, 32, 48, 64)
     assert np.array_equal(r.gemm_fused_cpu(a, b, bias, res), oracle.gemm_fused(a, b, bias, res))
+    if r.bgemm is not None and r.qk is not None:
+        ab, bb = rng.standard_normal((2, 19, 33)).astype(np.float32), rng.standard_normal((2, 33, 21)).astype(np.float32)
+        assert np.array_equal(r.gemm_batched_cpu(ab, bb), oracle.gemm_batched(ab, bb))
+        qq, kk = rng.standard_normal((3, 20, 24)).astype(np.float32), rng.standard_normal((3, 20, 24)).astype(np.float32)
+        assert np.array_equal(r.qk_cpu(qq, kk, 0.2041), oracle.qk_scores(qq, kk, 0.2041))
