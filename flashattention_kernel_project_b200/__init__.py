@@ -13,10 +13,12 @@ from .ops import (  # noqa: F401
     fa_forward_cross,
     fa_forward_partial,
     fa_forward_host,
+    fa_forward_unfused,
     gemm_batched,
     gemm_fused_epilogue,
     gemm_fused_epilogue_host,
     softmax_rows,
+    softmax_rows_f16out,
     softmax_rows_host,
     launch_count,
     last_debug,
@@ -25,6 +27,6 @@ from .sharding import shard_range, ring_attention, new_ring_group  # noqa: F401
 
 __all__ = [
     "FaError", "lib_path", "load_library", "fa_forward", "fa_forward_f32out", "fa_forward_cross", "fa_forward_partial",
-    "fa_forward_host", "gemm_batched", "gemm_fused_epilogue", "gemm_fused_epilogue_host", "softmax_rows",
+    "fa_forward_host", "gemm_batched", "fa_forward_unfused", "softmax_rows_f16out", "gemm_fused_epilogue", "gemm_fused_epilogue_host", "softmax_rows",
     "softmax_rows_host", "launch_count", "last_debug", "shard_range", "ring_attention", "new_ring_group",
 ]

@@ -22,6 +22,8 @@ SIGNATURES = {
     "gemm_fused_epilogue": (c_int, [c_void_p] * 5 + [c_int] * 3 + [c_void_p]),
     "gemm_batched": (c_int, [c_void_p] * 3 + [c_int] * 5 + [c_float, c_void_p]),
     "softmax_rows": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "softmax_rows_f16out": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "fa_forward_unfused": (c_int, [c_void_p] * 6 + [c_int] * 4 + [c_float, c_void_p]),
     "fa_forward_host": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_float]),
     "gemm_fused_epilogue_host": (c_int, [c_void_p] * 5 + [c_int] * 3),
     "softmax_rows_host": (c_int, [c_void_p, c_void_p, c_int, c_int]),

@@ -306,24 +306,26 @@ int run_gemm(const void* A, const void* Bm, const float* bias, const float* resi
 }
 
 // ---- softmax ------------------------------------------------------------------------------
-template <int TPR, int V4>
-void launch_softmax_reg(const float* X, float* P, int rows, int N, int sm_count, cudaStream_t s) {
+template <int TPR, int V4, typename TOut>
+void launch_softmax_reg(const float* X, TOut* P, int rows, int N, int sm_count, cudaStream_t s) {
   constexpr int kGroups = 256 / TPR;
   long long ctas = (static_cast<long long>(rows) + kGroups - 1) / kGroups;
   const long long cap = static_cast<long long>(sm_count) * 8;  // up to 8 resident CTAs per SM, grid-stride beyond
   if (ctas > cap) ctas = cap;
-  softmax_rows_reg_kernel<TPR, V4><<<static_cast<unsigned>(ctas), 256, 0, s>>>(X, P, rows, N);
+  softmax_rows_reg_kernel<TPR, V4, TOut><<<static_cast<unsigned>(ctas), 256, 0, s>>>(X, P, rows, N);
 }
 
-int run_softmax(const float* X, float* P, int rows, int N, void* stream) {
+template <typename TOut>
+int run_softmax(const float* X, TOut* P, int rows, int N, void* stream) {
   if (rows <= 0 || N <= 0) return FA_ERR_BAD_SHAPE;
   if (X == nullptr || P == nullptr) return FA_ERR_NULL_POINTER;
-  if ((reinterpret_cast<uintptr_t>(X) & 3u) || (reinterpret_cast<uintptr_t>(P) & 3u)) return FA_ERR_MISALIGNED;
+  if ((reinterpret_cast<uintptr_t>(X) & 3u) || (reinterpret_cast<uintptr_t>(P) & (sizeof(TOut) - 1))) return FA_ERR_MISALIGNED;
   DeviceState* st = nullptr;
   int rc = current_device_state(&st);
   if (rc != FA_OK) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const bool vec_ok = (N % 4 == 0) && aligned16(X) && aligned16(P);
+  // 128-bit loads of X and 4-element stores of P (16 B of float, 8 B of half)
+  const bool vec_ok = (N % 4 == 0) && aligned16(X) && (reinterpret_cast<uintptr_t>(P) & (4 * sizeof(TOut) - 1)) == 0;
   const int sm = st->sm_count;
   if (vec_ok && N <= 128) launch_softmax_reg<32, 1>(X, P, rows, N, sm, s);
   else if (vec_ok && N <= 256) launch_softmax_reg<32, 2>(X, P, rows, N, sm, s);
@@ -336,7 +338,7 @@ int run_softmax(const float* X, float* P, int rows, int N, void* stream) {
     long long ctas = rows;
     const long long cap = static_cast<long long>(sm) * 8;
     if (ctas > cap) ctas = cap;
-    softmax_rows_3pass_kernel<<<static_cast<unsigned>(ctas), 256, 0, s>>>(X, P, rows, N);
+    softmax_rows_3pass_kernel<TOut><<<static_cast<unsigned>(ctas), 256, 0, s>>>(X, P, rows, N);
   }
   g_launches.fetch_add(1, std::memory_order_relaxed);
   const cudaError_t e = cudaGetLastError();
@@ -441,6 +443,28 @@ int gemm_batched(const void* A, const void* Bm, float* C, int batch, int M, int 
 }
 
 int softmax_rows(const float* X, float* P, int rows, int N, void* stream) { return run_softmax(X, P, rows, N, stream); }
+
+int softmax_rows_f16out(const float* X, void* P, int rows, int N, void* stream) {
+  return run_softmax(X, static_cast<__half*>(P), rows, N, stream);
+}
+
+int fa_forward_unfused(const void* Q, const void* K, const void* V, float* O, float* S, void* P, int B, int H, int N,
+                       int D, float scale, void* stream) {
+  if (B <= 0 || H <= 0 || N <= 0 || D <= 0) return FA_ERR_BAD_SHAPE;
+  if (Q == nullptr || K == nullptr || V == nullptr || O == nullptr || S == nullptr || P == nullptr)
+    return FA_ERR_NULL_POINTER;
+  const long long bh = static_cast<long long>(B) * H;
+  if (bh > 0x7fffffffll || bh * N > 0x7fffffffll) return FA_ERR_BAD_SHAPE;
+  // stage A: S = scale * Q K^T  (K as [N, D] rows = the transposed-B form)
+  const GemmCall qk{Q, K, nullptr, nullptr, S, static_cast<int>(bh), N, N, D, true, false, scale};
+  int rc = run_gemm(qk, stream);
+  if (rc != FA_OK) return rc;
+  // stage B: P = softmax_rows(S), rounded to fp16 for the tensor core
+  if ((rc = run_softmax(S, static_cast<__half*>(P), static_cast<int>(bh * N), N, stream)) != FA_OK) return rc;
+  // stage C: O = P V
+  const GemmCall pv{P, V, nullptr, nullptr, O, static_cast<int>(bh), N, D, N, false, false, 1.0f};
+  return run_gemm(pv, stream);
+}
 
 int fa_forward_host(const void* Q, const void* K, const void* V, void* O, int B, int H, int N, int D, float scale) {
   if (B <= 0 || H <= 0 || N <= 0) return FA_ERR_BAD_SHAPE;

@@ -1,4 +1,4 @@
-// Row softmax, fp32 in / fp32 out, one HBM read and one HBM write per element.
+// Row softmax, fp32 in / fp32 (or fp16) out, one HBM read and one HBM write per element.
 //
 // Replaces softmax_naive_baseline_kernel (Softmax micro kernel/softmax_naive_baseline/
 // softmax_naive_baseline.cu:56-130): one 128-thread block per row, row staged in shared memory,
@@ -14,10 +14,23 @@
 // written back with 128-bit streaming stores.  Longer or unaligned rows take a three-pass
 // kernel whose 2nd/3rd passes hit L2.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
 namespace fa {
+
+// Output element: float (softmax_rows) or __half (softmax_rows_f16out, the P operand of a following P*V GEMM).
+__device__ __forceinline__ void store_probs4(float* p, int idx4, float4 v) { __stcs(reinterpret_cast<float4*>(p) + idx4, v); }
+__device__ __forceinline__ void store_probs4(__half* p, int idx4, float4 v) {
+  const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<const uint32_t*>(&lo);
+  u.y = *reinterpret_cast<const uint32_t*>(&hi);
+  __stcs(reinterpret_cast<uint2*>(p) + idx4, u);
+}
+__device__ __forceinline__ void store_prob(float* p, int i, float v) { p[i] = v; }
+__device__ __forceinline__ void store_prob(__half* p, int i, float v) { p[i] = __float2half_rn(v); }
 
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
@@ -32,8 +45,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // TPR threads cooperate on one row; each caches V4 float4 (element (i*TPR + t)*4, i < V4).
 // Requires N % 4 == 0, 16-byte aligned X and P, N <= TPR*V4*4.  blockDim.x = 256.
-template <int TPR, int V4>
-__global__ void __launch_bounds__(256) softmax_rows_reg_kernel(const float* X, float* P, int rows, int N) {
+template <int TPR, int V4, typename TOut>
+__global__ void __launch_bounds__(256) softmax_rows_reg_kernel(const float* X, TOut* P, int rows, int N) {
   static_assert(TPR == 32 || TPR == 256, "thread group is a warp or the CTA");
   constexpr int kGroupsPerCta = 256 / TPR;
   __shared__ float red[2][8];
@@ -43,7 +56,7 @@ __global__ void __launch_bounds__(256) softmax_rows_reg_kernel(const float* X, f
   for (long long row = static_cast<long long>(blockIdx.x) * kGroupsPerCta + g; row < rows;
        row += static_cast<long long>(gridDim.x) * kGroupsPerCta) {
     const float4* xin = reinterpret_cast<const float4*>(X + row * N);  // X == P allowed: a row is fully
-    float4* pout = reinterpret_cast<float4*>(P + row * N);             // read before any of it is written
+    TOut* pout = P + row * N;                                           // read before any of it is written
     float4 v[V4];
 #pragma unroll
     for (int i = 0; i < V4; ++i) {
@@ -82,19 +95,20 @@ __global__ void __launch_bounds__(256) softmax_rows_reg_kernel(const float* X, f
 #pragma unroll
     for (int i = 0; i < V4; ++i) {
       const int idx = i * TPR + t;
-      if (idx < n4) __stcs(pout + idx, make_float4(v[i].x * inv, v[i].y * inv, v[i].z * inv, v[i].w * inv));
+      if (idx < n4) store_probs4(pout, idx, make_float4(v[i].x * inv, v[i].y * inv, v[i].z * inv, v[i].w * inv));
     }
     if constexpr (TPR == 256) __syncthreads();  // red[] is reused by the next row
   }
 }
 
 // Any N, any alignment: one CTA per row, three passes (max, sum, write).
-__global__ void __launch_bounds__(256) softmax_rows_3pass_kernel(const float* X, float* P, int rows, int N) {
+template <typename TOut>
+__global__ void __launch_bounds__(256) softmax_rows_3pass_kernel(const float* X, TOut* P, int rows, int N) {
   __shared__ float red[8];
   __shared__ float bcast;
   for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
     const float* xin = X + row * N;  // no __restrict__: in-place (X == P) is allowed
-    float* pout = P + row * N;
+    TOut* pout = P + row * N;
     float m = -CUDART_INF_F;
     for (int i = threadIdx.x; i < N; i += 256) m = fmaxf(m, xin[i]);
     m = warp_max(m);
@@ -120,7 +134,7 @@ __global__ void __launch_bounds__(256) softmax_rows_3pass_kernel(const float* X,
     }
     __syncthreads();
     const float inv = 1.f / bcast;
-    for (int i = threadIdx.x; i < N; i += 256) pout[i] = expf(xin[i] - m) * inv;
+    for (int i = threadIdx.x; i < N; i += 256) store_prob(pout, i, expf(xin[i] - m) * inv);
     __syncthreads();
   }
 }

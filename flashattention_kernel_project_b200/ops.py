@@ -7,6 +7,7 @@ flat (B*H) batches of row-major [N, D] matrices, explicit `scale`, epilogue orde
 bias -> ReLU -> residual with nullable bias / residual.
 """
 import ctypes
+import math
 
 import numpy as np
 import torch
@@ -178,6 +179,47 @@ def softmax_rows(x, out=None, stream=None):
         check(lib.softmax_rows(_dev_ptr(x, torch.float32, "X"), _dev_ptr(out, torch.float32, "P"), rows, N,
                                _stream_ptr(stream)), "softmax_rows")
     return out
+
+
+def softmax_rows_f16out(x, out=None, stream=None):
+    """Row softmax with fp16 output (feeds the P*V GEMM of the unfused pipeline)."""
+    _require_cuda(x, "X")
+    if x.dim() != 2:
+        raise ValueError("expected a [rows, N] tensor")
+    rows, N = int(x.shape[0]), int(x.shape[1])
+    if out is None:
+        out = torch.empty((rows, N), dtype=torch.float16, device=x.device)
+    lib = load_library()
+    with torch.cuda.device(x.device):
+        check(lib.softmax_rows_f16out(_dev_ptr(x, torch.float32, "X"), _dev_ptr(out, torch.float16, "P"), rows, N,
+                                      _stream_ptr(stream)), "softmax_rows_f16out")
+    return out
+
+
+def fa_forward_unfused(q, k, v, scale=None, workspace=None, stream=None):
+    """Attention through materialised scores (QK^T GEMM -> row softmax -> PV GEMM); fp32 [B,H,N,D].
+
+    workspace: optional (S fp32 [B*H,N,N], P fp16 [B*H,N,N]) pair to reuse; returned as the second value."""
+    _require_cuda(q, "Q")
+    if q.dim() != 4 or k.shape != q.shape or v.shape != q.shape:
+        raise ValueError("Q, K, V must be [B, H, N, D] of one shape")
+    B, H, N, D = (int(x) for x in q.shape)
+    if scale is None:
+        scale = 1.0 / math.sqrt(D)
+    out = torch.empty((B, H, N, D), dtype=torch.float32, device=q.device)
+    if workspace is None:
+        workspace = (torch.empty((B * H, N, N), dtype=torch.float32, device=q.device),
+                     torch.empty((B * H, N, N), dtype=torch.float16, device=q.device))
+    S, P = workspace
+    if tuple(S.shape) != (B * H, N, N) or tuple(P.shape) != (B * H, N, N):
+        raise ValueError("workspace must be (fp32 [B*H,N,N], fp16 [B*H,N,N])")
+    lib = load_library()
+    with torch.cuda.device(q.device):
+        check(lib.fa_forward_unfused(_dev_ptr(q, torch.float16, "Q"), _dev_ptr(k, torch.float16, "K"),
+                                     _dev_ptr(v, torch.float16, "V"), _dev_ptr(out, torch.float32, "O"),
+                                     _dev_ptr(S, torch.float32, "S"), _dev_ptr(P, torch.float16, "P"), B, H, N, D,
+                                     float(scale), _stream_ptr(stream)), "fa_forward_unfused")
+    return out, workspace
 
 
 # ----------------------------- host-buffer variants ------------------------------------

@@ -117,6 +117,23 @@ int gemm_batched(const void* A, const void* Bm, float* C, int batch, int M, int 
  */
 int softmax_rows(const float* X, float* P, int rows, int N, void* stream);
 
+/* Same, fp16 output (the A operand of a following P*V GEMM); X and P must not overlap. */
+int softmax_rows_f16out(const float* X, void* P, int rows, int N, void* stream);
+
+/*
+ * Attention through MATERIALISED scores, three launches on `stream`:
+ *   S = scale * Q K^T (gemm_batched, trans_b) -> P = softmax_rows_f16out(S) -> O = P V (gemm_batched).
+ *   Q, K, V fp16 [B,H,N,D]; O fp32 [B,H,N,D]; workspaces owned by the caller: S fp32 [B*H,N,N], P fp16 [B*H,N,N].
+ *   N % 8 == 0 and D % 8 == 0 (16-byte row pitches); any D.
+ * This is the reference's unfused pipeline -- QK_wmma_kernel (GEMM/QK Tensor Core/qk_wmma_5_1_2.cu:32-38), a row
+ * softmax, a second WMMA GEMM -- whose per-stage cost its latency study measures
+ * (FlashAttention/flashattn_forward_memory_bound/flashattn_stage_latency_breakdown.cu:212-424).  It moves
+ * 6*N*N bytes per (b,h) through HBM that fa_forward never writes; it exists as the independent second
+ * implementation the fused kernel is checked against at full size, and to reproduce that study on a B200.
+ */
+int fa_forward_unfused(const void* Q, const void* K, const void* V, float* O, float* S, void* P, int B, int H, int N,
+                       int D, float scale, void* stream);
+
 /*
  * Host-buffer variants: the flow of the reference's main() (cudaMalloc -> H2D -> launch -> D2H,
  * e.g. flashattn_streaming_16x32_2warp_softmax_v12i.cu:325-368) behind one call.  All pointers
