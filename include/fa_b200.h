@@ -78,8 +78,9 @@ int fa_forward_cross(const void* Q, const void* K, const void* V, float* O, int 
  * with the merge rule the reference applies tile to tile
  *   (Streaming_FlashAttention_Forward_Kernel/flashattn_streaming_16x16.cu:247-261).
  * is_first != 0: the incoming state is ignored (treated as empty).
- * is_last  != 0: additionally writes the normalised result to O_final (fp16 [B,H,Nq,D]);
- *                O_final may be NULL otherwise.
+ * is_last  != 0: the merged result is normalised and written to O_final (fp16 [B,H,Nq,D]) INSTEAD of
+ *                the state -- (O_acc, m, l) are consumed and left as they were (no 4x-wider fp32 write
+ *                on the step that ends the ring).  O_final may be NULL when is_last == 0.
  * The reference has no multi-GPU path; this entry exists for BASELINE config 4.
  */
 int fa_forward_partial(const void* Q, const void* K, const void* V, float* O_acc, float* m, float* l,

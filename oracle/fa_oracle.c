@@ -391,6 +391,123 @@ void fa_oracle_qk_scores(const float* Q, const float* Kmat, float* S, int BH, in
 }
 
 /* ---------------------------------------------------------------------------------------
+ * The streaming family's host oracle: S = (Q K) * scale materialised, row softmax with the
+ * `+EPS` normaliser (EPS = 1e-6), O = P V -- restates flashattn_streaming_cpu_ref
+ * (Streaming_FlashAttention_Forward_Kernel/flashattn_streaming_16x16.cu:280-348).
+ * Layouts as in that file: Q half [B, M, Kd], K half [B, Kd, L] (TRANSPOSED: key index fastest),
+ * V half [B, L, Dv]; the file fixes M = Kd = Dv = 16, the restatement keeps them as arguments.
+ * ------------------------------------------------------------------------------------- */
+void fa_oracle_streaming_ref_f16(const uint16_t* Q, const uint16_t* Kt, const uint16_t* V, float* O, int B, int M, int L,
+                                 int Kd, int Dv, float scale) {
+  const float NEG_LARGE = -1e30f, EPS = 1e-6f;
+  float* S = (float*)malloc(sizeof(float) * (size_t)M * L);
+  float* P = (float*)malloc(sizeof(float) * (size_t)M * L);
+  for (int b = 0; b < B; ++b) {
+    const uint16_t* Qb = Q + (size_t)b * M * Kd;
+    const uint16_t* Kb = Kt + (size_t)b * Kd * L;
+    const uint16_t* Vb = V + (size_t)b * L * Dv;
+    float* Ob = O + (size_t)b * M * Dv;
+    for (int i = 0; i < M; ++i)
+      for (int j = 0; j < L; ++j) {
+        float acc = 0.0f;
+        for (int k = 0; k < Kd; ++k) acc += half_bits_to_float(Qb[i * Kd + k]) * half_bits_to_float(Kb[(size_t)k * L + j]);
+        S[(size_t)i * L + j] = acc * scale;
+      }
+    for (int i = 0; i < M; ++i) {
+      float maxv = NEG_LARGE;
+      for (int j = 0; j < L; ++j)
+        if (S[(size_t)i * L + j] > maxv) maxv = S[(size_t)i * L + j];
+      float sumv = 0.0f;
+      for (int j = 0; j < L; ++j) {
+        const float e = expf(S[(size_t)i * L + j] - maxv);
+        P[(size_t)i * L + j] = e;
+        sumv += e;
+      }
+      const float inv = 1.0f / (sumv + EPS);
+      for (int j = 0; j < L; ++j) P[(size_t)i * L + j] *= inv;
+    }
+    for (int i = 0; i < M; ++i)
+      for (int d = 0; d < Dv; ++d) {
+        float acc = 0.0f;
+        for (int j = 0; j < L; ++j) acc += P[(size_t)i * L + j] * half_bits_to_float(Vb[(size_t)j * Dv + d]);
+        Ob[i * Dv + d] = acc;
+      }
+  }
+  free(S);
+  free(P);
+}
+
+/* ---------------------------------------------------------------------------------------
+ * STAGE oracle: the streaming (online-softmax) state after every key tile.  Per tile of `tile`
+ * keys: m_t = max_j s_ij, l_t = sum_j exp(s_ij - m_t), y_t[d] = sum_j exp(s_ij - m_t) v_jd; then
+ * the tile-to-tile merge  m' = max(m, m_t), alpha = exp(m - m'), beta = exp(m_t - m'),
+ * l' = l alpha + l_t beta, y' = y alpha + y_t beta, with the first tile copied and empty tiles
+ * skipped -- restates the kernel-side rule of
+ * Streaming_FlashAttention_Forward_Kernel/flashattn_streaming_16x16.cu:170-261 (tile statistics
+ * :186-223, merge :228-261; `__expf` there, expf here; warp-butterfly sums there, j-ascending
+ * here).  Q [B,M,D], K [B,L,D] (row per key), V [B,L,Dv] half.  Outputs hold one snapshot per tile:
+ * m, l [T, B, M], y [T, B, M, Dv] with T = ceil(L / tile); the last tile may be partial.
+ * The reference has no host function for this rule (it lives in device code only): the
+ * restatement is pinned through its invariants -- y/l of the last snapshot equals cpu_reference,
+ * m equals the running row max, snapshots do not depend on the tile size beyond rounding -- and
+ * against the reference's own streaming kernel run on the GPU (tests/test_gpu_stage_ladder.py).
+ * ------------------------------------------------------------------------------------- */
+void fa_oracle_streaming_state_f16(const uint16_t* Q, const uint16_t* K, const uint16_t* V, float* m_out, float* l_out,
+                                   float* y_out, int B, int M, int L, int D, int Dv, int tile, float scale) {
+  const float NEG_LARGE = -1e30f;
+  const int T = (L + tile - 1) / tile;
+  float* s = (float*)malloc(sizeof(float) * (size_t)tile);
+  float* yt = (float*)malloc(sizeof(float) * (size_t)Dv);
+  float* y = (float*)malloc(sizeof(float) * (size_t)Dv);
+  for (int b = 0; b < B; ++b) {
+    for (int i = 0; i < M; ++i) {
+      const uint16_t* q = Q + ((size_t)b * M + i) * D;
+      float m = NEG_LARGE, l = 0.0f;
+      for (int d = 0; d < Dv; ++d) y[d] = 0.0f;
+      for (int t = 0; t < T; ++t) {
+        const int j0 = t * tile, j1 = (j0 + tile < L) ? j0 + tile : L;
+        float mt = NEG_LARGE;
+        for (int j = j0; j < j1; ++j) {
+          const uint16_t* k = K + ((size_t)b * L + j) * D;
+          float acc = 0.0f;
+          for (int c = 0; c < D; ++c) acc += half_bits_to_float(q[c]) * half_bits_to_float(k[c]);
+          s[j - j0] = acc * scale;
+          mt = fmaxf(mt, s[j - j0]);
+        }
+        float lt = 0.0f;
+        for (int d = 0; d < Dv; ++d) yt[d] = 0.0f;
+        for (int j = j0; j < j1; ++j) {
+          const float e = expf(s[j - j0] - mt);
+          lt += e;
+          const uint16_t* v = V + ((size_t)b * L + j) * Dv;
+          for (int d = 0; d < Dv; ++d) yt[d] += e * half_bits_to_float(v[d]);
+        }
+        if (lt > 0.0f) {
+          if (m == NEG_LARGE) {
+            m = mt;
+            l = lt;
+            for (int d = 0; d < Dv; ++d) y[d] = yt[d];
+          } else {
+            const float mn = fmaxf(m, mt);
+            const float alpha = expf(m - mn), beta = expf(mt - mn);
+            l = l * alpha + lt * beta;
+            for (int d = 0; d < Dv; ++d) y[d] = y[d] * alpha + yt[d] * beta;
+            m = mn;
+          }
+        }
+        const size_t row = ((size_t)t * B + b) * M + i;
+        m_out[row] = m;
+        l_out[row] = l;
+        for (int d = 0; d < Dv; ++d) y_out[row * Dv + d] = y[d];
+      }
+    }
+  }
+  free(s);
+  free(yt);
+  free(y);
+}
+
+/* ---------------------------------------------------------------------------------------
  * Error metrics, adopted verbatim: rel_l2 = sqrt(sum (a-b)^2 / (sum b^2 + 1e-30))
  * (flashattn_streaming_16x32_2warp_softmax_v12i.cu:288-296); max_abs = max |a-b| in double
  * (tensorcore_gemm_fused_epilogue.cu:247-254).

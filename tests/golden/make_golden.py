@@ -58,6 +58,11 @@ def main():
     qq = rng2.uniform(-1, 1, (2, 48, 64)).astype(np.float16).astype(np.float32)
     kk = rng2.uniform(-1, 1, (2, 48, 64)).astype(np.float16).astype(np.float32)
     np.savez_compressed(os.path.join(HERE, "qk_scores.npz"), q=qq, k=kk, s=r.qk_cpu(qq, kk, 0.125), scale=np.float32(0.125))
+    # the streaming family's fixture and oracle: mt19937(42) normal(0,1), order Q,K,V, K stored [B,16,L], `+1e-6`
+    # normaliser, scale 1/4 (Streaming_FlashAttention_Forward_Kernel/flashattn_streaming_16x16.cu:280-348,365-380); B reduced
+    q, kt, v = r.streaming16_fill(42, 24, 128)
+    np.savez_compressed(os.path.join(HERE, "attn_streaming16.npz"), q=q.view(np.uint16), kt=kt.view(np.uint16),
+                        v=v.view(np.uint16), o=r.streaming16_cpu(q, kt, v, 0.25), scale=np.float32(0.25))
     # row softmax through flashattn_ref with K = V = I, scale = 1 (its softmax step, :242-252)
     n = 48
     x = (rng.standard_normal((1, n, n)) * 3).astype(np.float32)

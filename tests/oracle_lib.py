@@ -47,6 +47,8 @@ class Oracle:
         L.fa_oracle_gemm_fused_f16.argtypes = [_u16p, _u16p, ctypes.c_void_p, ctypes.c_void_p, _f32p] + [c_int] * 6
         L.fa_oracle_gemm_batched.argtypes = [_f32p, _f32p, _f32p] + [c_int] * 5
         L.fa_oracle_qk_scores.argtypes = [_f32p, _f32p, _f32p] + [c_int] * 4 + [c_float, c_int]
+        L.fa_oracle_streaming_ref_f16.argtypes = [_u16p, _u16p, _u16p, _f32p] + [c_int] * 5 + [c_float]
+        L.fa_oracle_streaming_state_f16.argtypes = [_u16p, _u16p, _u16p, _f32p, _f32p, _f32p] + [c_int] * 6 + [c_float]
         L.fa_oracle_rel_l2.argtypes = [_f32p, _f32p, c_size_t]
         L.fa_oracle_rel_l2.restype = c_double
         L.fa_oracle_max_abs.argtypes = [_f32p, _f32p, c_size_t]
@@ -137,6 +139,25 @@ class Oracle:
         self.L.fa_oracle_qk_scores(q, k, out, BH, N, Nk, D, float(scale), nthreads)
         return out
 
+    def streaming_ref_f16(self, q, kt, v, scale):
+        """q [B,M,Kd], kt [B,Kd,L] (transposed K, as the streaming family stores it), v [B,L,Dv] fp16 -> fp32 [B,M,Dv];
+        `+1e-6` normaliser (flashattn_streaming_cpu_ref)."""
+        B, M, Kd = q.shape
+        L, Dv = v.shape[1], v.shape[2]
+        out = np.empty((B, M, Dv), dtype=np.float32)
+        self.L.fa_oracle_streaming_ref_f16(_as_u16(q), _as_u16(kt), _as_u16(v), out, B, M, L, Kd, Dv, float(scale))
+        return out
+
+    def streaming_state_f16(self, q, k, v, tile, scale):
+        """Online-softmax state after every key tile: (m, l) [T,B,M], y [T,B,M,Dv]; q [B,M,D], k [B,L,D], v [B,L,Dv]."""
+        B, M, D = q.shape
+        L, Dv = k.shape[1], v.shape[2]
+        T = (L + tile - 1) // tile
+        m, l = np.empty((T, B, M), np.float32), np.empty((T, B, M), np.float32)
+        y = np.empty((T, B, M, Dv), np.float32)
+        self.L.fa_oracle_streaming_state_f16(_as_u16(q), _as_u16(k), _as_u16(v), m, l, y, B, M, L, D, Dv, tile, float(scale))
+        return m, l, y
+
     def rel_l2(self, a, b):
         a = np.ascontiguousarray(a, dtype=np.float32).ravel()
         b = np.ascontiguousarray(b, dtype=np.float32).ravel()
@@ -201,6 +222,10 @@ class RefCpu:
         self.qk = RefLib("qk_wmma").L if ref_available("qk_wmma") else None
         if self.qk is not None:
             self.qk.ref_qk_cpu.argtypes = [_f32p] * 3 + [c_int] * 3 + [c_float]
+        self.st16 = RefLib("streaming16").L if ref_available("streaming16") else None
+        if self.st16 is not None:
+            self.st16.ref_streaming16_cpu.argtypes = [_u16p, _u16p, _u16p, _f32p, c_int, c_int, c_float]
+            self.st16.ref_streaming16_fill.argtypes = [ctypes.c_uint, _u16p, c_size_t, _u16p, c_size_t, _u16p, c_size_t]
 
     def v12i_cpu_reference(self, q, k, v, scale):
         B, M, KD = q.shape
@@ -267,6 +292,18 @@ class RefCpu:
                            BH, N, D, float(scale))
         return out
 
+    def streaming16_cpu(self, q, kt, v, scale):
+        """q [B,16,16], kt [B,16,L], v [B,L,16] fp16 -> fp32 [B,16,16]."""
+        B, L = q.shape[0], v.shape[1]
+        out = np.empty((B, 16, 16), dtype=np.float32)
+        self.st16.ref_streaming16_cpu(_as_u16(q), _as_u16(kt), _as_u16(v), out, B, L, float(scale))
+        return out
+
+    def streaming16_fill(self, seed, B, L):
+        q, kt, v = np.empty((B, 16, 16), np.uint16), np.empty((B, 16, L), np.uint16), np.empty((B, L, 16), np.uint16)
+        self.st16.ref_streaming16_fill(seed, q, q.size, kt, kt.size, v, v.size)
+        return q.view(np.float16), kt.view(np.float16), v.view(np.float16)
+
     def gemm_fused_fill(self, seed, M, N, K):
         a, b = np.empty((M, K), np.float32), np.empty((K, N), np.float32)
         bias, res = np.empty((N,), np.float32), np.empty((M, N), np.float32)
@@ -295,6 +332,8 @@ class RefGpu:
         self.bgemm.ref_gemm_batched_launch.argtypes = [vp, vp, vp, c_int, c_int, c_int, c_int, vp]
         self.qk = RefLib("qk_wmma").L
         self.qk.ref_qk_launch.argtypes = [vp, vp, vp, c_int, c_int, c_int, c_float, vp]
+        self.st16 = RefLib("streaming16").L
+        self.st16.ref_streaming16_launch.argtypes = [vp, vp, vp, vp, c_int, c_int, c_float, vp]
 
     @staticmethod
     def _chk(rc, what):
@@ -342,3 +381,8 @@ class RefGpu:
         BH, N, D = q.shape
         self._chk(self.qk.ref_qk_launch(q.data_ptr(), k.data_ptr(), out.data_ptr(), BH, N, D, float(scale), stream),
                   "qk_wmma")
+
+    def streaming16(self, q, kt, v, out, scale, stream=0):
+        """q [B,16,16], kt [B,16,L] (transposed K), v [B,L,16] fp16 device tensors -> out fp32 [B,16,16]."""
+        self._chk(self.st16.ref_streaming16_launch(q.data_ptr(), kt.data_ptr(), v.data_ptr(), out.data_ptr(), q.shape[0],
+                                                   v.shape[1], float(scale), stream), "streaming16")

@@ -93,6 +93,42 @@ def test_gemm_batched_and_qk_scores_match_golden(oracle, golden):
     assert np.array_equal(s2, s[:, :, :17])
 
 
+def test_streaming_family_oracle_matches_golden(oracle, golden):
+    g = golden("attn_streaming16.npz")
+    q, kt, v = (g[n].view(np.float16) for n in ("q", "kt", "v"))
+    o = oracle.streaming_ref_f16(q, kt, v, float(g["scale"]))
+    assert np.array_equal(o, g["o"])
+    # the `+1e-6` normaliser and the materialised P differ from cpu_reference (no EPS) far below the tolerance
+    k = np.ascontiguousarray(kt.transpose(0, 2, 1))
+    plain = oracle.attention_f16(q, k, v, float(g["scale"]))
+    assert oracle.max_abs(o, plain) < 2e-6 and oracle.rel_l2(o, plain) < 2e-6
+
+
+@pytest.mark.parametrize("tile", [16, 128, 50])
+def test_stage_oracle_streaming_state_invariants(oracle, golden, tile):
+    """(m, l, y) after every key tile: m is the running row max, y/l the attention over the prefix, and the snapshots at
+    common prefix lengths do not depend on the tile size."""
+    g = golden("attn_ragged_d128.npz")  # [2, 200, 128], scale 1/sqrt(128)
+    q, k, v = (g[n].view(np.float16) for n in ("q", "k", "v"))
+    scale = float(g["scale"])
+    m, l, y = oracle.streaming_state_f16(q, k, v, tile, scale)
+    T = (200 + tile - 1) // tile
+    assert m.shape == (T, 2, 200) and y.shape == (T, 2, 200, 128)
+    s = oracle.qk_scores(q.astype(np.float32), k.astype(np.float32), 1.0)  # double accumulate, then one rounding
+    for t in range(T):
+        end = min(200, (t + 1) * tile)
+        prefix = oracle.attention_f16(q, k[:, :end], v[:, :end], scale)
+        assert oracle.rel_l2(y[t] / l[t][..., None], prefix) < 5e-6
+        assert np.allclose(m[t], (s[:, :, :end] * np.float32(scale)).max(axis=-1), rtol=0, atol=2e-6)
+        assert (l[t] >= 1.0 - 1e-6).all()  # the max element contributes exp(0) = 1
+    # last snapshot == full attention == the committed golden output of the reference's cpu_reference
+    assert oracle.rel_l2(y[-1] / l[-1][..., None], g["o"]) < 5e-6
+    if tile != 50:
+        m50, l50, y50 = oracle.streaming_state_f16(q, k, v, 200, scale)  # a single tile: no merge at all
+        assert np.array_equal(m[-1], m50[0])
+        assert np.allclose(l[-1], l50[0], rtol=1e-5) and np.allclose(y[-1], y50[0], rtol=1e-4, atol=1e-5)
+
+
 def test_softmax_rows_matches_golden(oracle, golden):
     g = golden("softmax_rows.npz")
     p = oracle.softmax_rows(g["x"])
@@ -141,6 +177,9 @@ def test_oracle_bit_exact_against_compiled_reference(oracle):
     assert np.array_equal(r.softmax_block_flashattn_ref(qf, kf, vf, 0.7), oracle.attention_f32(qf, kf, vf, 0.7))
     a, b, bias, res = r.gemm_fused_fill(43, 32, 48, 64)
     assert np.array_equal(r.gemm_fused_cpu(a, b, bias, res), oracle.gemm_fused(a, b, bias, res))
+    if r.st16 is not None:
+        q, kt, v = r.streaming16_fill(7, 5, 64)
+        assert np.array_equal(r.streaming16_cpu(q, kt, v, 0.25), oracle.streaming_ref_f16(q, kt, v, 0.25))
     if r.bgemm is not None and r.qk is not None:
         ab, bb = rng.standard_normal((2, 19, 33)).astype(np.float32), rng.standard_normal((2, 33, 21)).astype(np.float32)
         assert np.array_equal(r.gemm_batched_cpu(ab, bb), oracle.gemm_batched(ab, bb))
