@@ -72,7 +72,12 @@ struct DeviceState {
   // scratch for the *_host entry points
   void* scratch[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   size_t scratch_bytes[6] = {0, 0, 0, 0, 0, 0};
+  // the *_host entry points pipeline H2D copy / kernel / D2H copy over chunks of the batch on three streams
+  bool pipe_ready = false;
+  cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
+  cudaEvent_t ev_in[16], ev_run[16];
 };
+constexpr int kHostChunksMax = 16;
 DeviceState g_dev[kMaxDevices];
 std::mutex g_mutex;
 unsigned int* g_dbg_host = nullptr;  // mapped pinned page shared by all devices
@@ -365,6 +370,37 @@ int scratch_get(DeviceState* st, int slot, size_t bytes, void** out) {
     if (e__ != cudaSuccess) return static_cast<int>(e__); \
   } while (0)
 
+// Streams and events of the host-buffer pipeline, created once per device.
+int host_pipe_init(DeviceState* st) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  if (st->pipe_ready) return FA_OK;
+  FA_CUDA_TRY(cudaStreamCreateWithFlags(&st->s_in, cudaStreamNonBlocking));
+  FA_CUDA_TRY(cudaStreamCreateWithFlags(&st->s_run, cudaStreamNonBlocking));
+  FA_CUDA_TRY(cudaStreamCreateWithFlags(&st->s_out, cudaStreamNonBlocking));
+  for (int i = 0; i < kHostChunksMax; ++i) {
+    FA_CUDA_TRY(cudaEventCreateWithFlags(&st->ev_in[i], cudaEventDisableTiming));
+    FA_CUDA_TRY(cudaEventCreateWithFlags(&st->ev_run[i], cudaEventDisableTiming));
+  }
+  st->pipe_ready = true;
+  return FA_OK;
+}
+// Everything enqueued by a *_host call has finished when this returns (also on its error paths, so that no copy is
+// still reading or writing the caller's buffers).
+int host_pipe_drain(DeviceState* st) {
+  const cudaError_t a = cudaStreamSynchronize(st->s_in), b = cudaStreamSynchronize(st->s_run),
+                    c = cudaStreamSynchronize(st->s_out);
+  if (a != cudaSuccess) return static_cast<int>(a);
+  if (b != cudaSuccess) return static_cast<int>(b);
+  return c == cudaSuccess ? FA_OK : static_cast<int>(c);
+}
+// Chunks of >= 8 MB of traffic each, at most kHostChunksMax and at most one per unit.
+int host_chunks(size_t total_bytes, long long units) {
+  long long n = static_cast<long long>(total_bytes >> 23);
+  if (n > kHostChunksMax) n = kHostChunksMax;
+  if (n > units) n = units;
+  return n < 1 ? 1 : static_cast<int>(n);
+}
+
 }  // namespace
 
 // =========================================== C ABI ==========================================
@@ -470,22 +506,40 @@ int fa_forward_host(const void* Q, const void* K, const void* V, void* O, int B,
   if (B <= 0 || H <= 0 || N <= 0) return FA_ERR_BAD_SHAPE;
   if (D != 64 && D != 128) return FA_ERR_BAD_HEAD_DIM;
   if (Q == nullptr || K == nullptr || V == nullptr || O == nullptr) return FA_ERR_NULL_POINTER;
+  const long long bh = static_cast<long long>(B) * H;
+  if (bh > 0x7fffffffll) return FA_ERR_BAD_SHAPE;
   DeviceState* st = nullptr;
   int rc = current_device_state(&st);
   if (rc != FA_OK) return rc;
-  const size_t bytes = static_cast<size_t>(B) * H * N * D * 2;
+  if ((rc = host_pipe_init(st)) != FA_OK) return rc;
+  const size_t unit = static_cast<size_t>(N) * D * 2;  // bytes of one (b,h) of one tensor
+  const size_t bytes = static_cast<size_t>(bh) * unit;
   void *dq, *dk, *dv, *dout;
   if ((rc = scratch_get(st, 0, bytes, &dq)) != FA_OK) return rc;
   if ((rc = scratch_get(st, 1, bytes, &dk)) != FA_OK) return rc;
   if ((rc = scratch_get(st, 2, bytes, &dv)) != FA_OK) return rc;
   if ((rc = scratch_get(st, 3, bytes, &dout)) != FA_OK) return rc;
-  FA_CUDA_TRY(cudaMemcpyAsync(dq, Q, bytes, cudaMemcpyHostToDevice, 0));
-  FA_CUDA_TRY(cudaMemcpyAsync(dk, K, bytes, cudaMemcpyHostToDevice, 0));
-  FA_CUDA_TRY(cudaMemcpyAsync(dv, V, bytes, cudaMemcpyHostToDevice, 0));
-  if ((rc = fa_forward(dq, dk, dv, dout, B, H, N, D, scale, nullptr)) != FA_OK) return rc;
-  FA_CUDA_TRY(cudaMemcpyAsync(O, dout, bytes, cudaMemcpyDeviceToHost, 0));
-  FA_CUDA_TRY(cudaStreamSynchronize(0));
-  return FA_OK;
+  // (b,h) units are independent: while chunk c runs, chunk c+1 is on its way in and chunk c-1 on its way out
+  // (PCIe is full duplex), so the call costs about the larger of the two copy directions, not their sum + kernel.
+  const int nchunk = host_chunks(bytes, bh);
+  for (int c = 0; c < nchunk; ++c) {
+    const long long u0 = bh * c / nchunk, u1 = bh * (c + 1) / nchunk;
+    const size_t off = static_cast<size_t>(u0) * unit, len = static_cast<size_t>(u1 - u0) * unit;
+    FA_CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(dq) + off, static_cast<const char*>(Q) + off, len, cudaMemcpyHostToDevice, st->s_in));
+    FA_CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(dk) + off, static_cast<const char*>(K) + off, len, cudaMemcpyHostToDevice, st->s_in));
+    FA_CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(dv) + off, static_cast<const char*>(V) + off, len, cudaMemcpyHostToDevice, st->s_in));
+    FA_CUDA_TRY(cudaEventRecord(st->ev_in[c], st->s_in));
+    FA_CUDA_TRY(cudaStreamWaitEvent(st->s_run, st->ev_in[c], 0));
+    if ((rc = fa_forward(static_cast<char*>(dq) + off, static_cast<char*>(dk) + off, static_cast<char*>(dv) + off,
+                         static_cast<char*>(dout) + off, 1, static_cast<int>(u1 - u0), N, D, scale, st->s_run)) != FA_OK) {
+      host_pipe_drain(st);
+      return rc;
+    }
+    FA_CUDA_TRY(cudaEventRecord(st->ev_run[c], st->s_run));
+    FA_CUDA_TRY(cudaStreamWaitEvent(st->s_out, st->ev_run[c], 0));
+    FA_CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(O) + off, static_cast<char*>(dout) + off, len, cudaMemcpyDeviceToHost, st->s_out));
+  }
+  return host_pipe_drain(st);
 }
 
 int gemm_fused_epilogue_host(const void* A, const void* Bm, const float* bias, const float* residual, float* C, int M,
@@ -495,28 +549,46 @@ int gemm_fused_epilogue_host(const void* A, const void* Bm, const float* bias, c
   DeviceState* st = nullptr;
   int rc = current_device_state(&st);
   if (rc != FA_OK) return rc;
+  if ((rc = host_pipe_init(st)) != FA_OK) return rc;
   const size_t ab = static_cast<size_t>(M) * K * 2, bb = static_cast<size_t>(K) * N * 2;
   const size_t cb = static_cast<size_t>(M) * N * 4, biasb = static_cast<size_t>(N) * 4;
   void *da, *db, *dbias = nullptr, *dres = nullptr, *dc;
   if ((rc = scratch_get(st, 0, ab, &da)) != FA_OK) return rc;
   if ((rc = scratch_get(st, 1, bb, &db)) != FA_OK) return rc;
   if ((rc = scratch_get(st, 3, cb, &dc)) != FA_OK) return rc;
-  FA_CUDA_TRY(cudaMemcpyAsync(da, A, ab, cudaMemcpyHostToDevice, 0));
-  FA_CUDA_TRY(cudaMemcpyAsync(db, Bm, bb, cudaMemcpyHostToDevice, 0));
-  if (bias != nullptr) {
-    if ((rc = scratch_get(st, 4, biasb, &dbias)) != FA_OK) return rc;
-    FA_CUDA_TRY(cudaMemcpyAsync(dbias, bias, biasb, cudaMemcpyHostToDevice, 0));
+  if (bias != nullptr && (rc = scratch_get(st, 4, biasb, &dbias)) != FA_OK) return rc;
+  if (residual != nullptr && (rc = scratch_get(st, 2, cb, &dres)) != FA_OK) return rc;
+  // B and bias are shared by every row block and go first; then row blocks of A / residual / C are pipelined
+  FA_CUDA_TRY(cudaMemcpyAsync(db, Bm, bb, cudaMemcpyHostToDevice, st->s_in));
+  if (bias != nullptr) FA_CUDA_TRY(cudaMemcpyAsync(dbias, bias, biasb, cudaMemcpyHostToDevice, st->s_in));
+  const long long row_blocks = (static_cast<long long>(M) + 255) / 256;  // chunks are whole 256-row output tiles
+  const int nchunk = host_chunks(ab + 2 * cb, row_blocks);
+  for (int c = 0; c < nchunk; ++c) {
+    const long long r0 = row_blocks * c / nchunk * 256;
+    long long r1 = row_blocks * (c + 1) / nchunk * 256;
+    if (r1 > M) r1 = M;
+    const int rows = static_cast<int>(r1 - r0);
+    const size_t a_off = static_cast<size_t>(r0) * K * 2, c_off = static_cast<size_t>(r0) * N * 4;
+    FA_CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(da) + a_off, static_cast<const char*>(A) + a_off,
+                                static_cast<size_t>(rows) * K * 2, cudaMemcpyHostToDevice, st->s_in));
+    if (residual != nullptr)
+      FA_CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(dres) + c_off, reinterpret_cast<const char*>(residual) + c_off,
+                                  static_cast<size_t>(rows) * N * 4, cudaMemcpyHostToDevice, st->s_in));
+    FA_CUDA_TRY(cudaEventRecord(st->ev_in[c], st->s_in));
+    FA_CUDA_TRY(cudaStreamWaitEvent(st->s_run, st->ev_in[c], 0));
+    rc = gemm_fused_epilogue(static_cast<char*>(da) + a_off, db, static_cast<const float*>(dbias),
+                             residual != nullptr ? reinterpret_cast<const float*>(static_cast<char*>(dres) + c_off) : nullptr,
+                             reinterpret_cast<float*>(static_cast<char*>(dc) + c_off), rows, N, K, st->s_run);
+    if (rc != FA_OK) {
+      host_pipe_drain(st);
+      return rc;
+    }
+    FA_CUDA_TRY(cudaEventRecord(st->ev_run[c], st->s_run));
+    FA_CUDA_TRY(cudaStreamWaitEvent(st->s_out, st->ev_run[c], 0));
+    FA_CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<char*>(C) + c_off, static_cast<char*>(dc) + c_off,
+                                static_cast<size_t>(rows) * N * 4, cudaMemcpyDeviceToHost, st->s_out));
   }
-  if (residual != nullptr) {
-    if ((rc = scratch_get(st, 2, cb, &dres)) != FA_OK) return rc;
-    FA_CUDA_TRY(cudaMemcpyAsync(dres, residual, cb, cudaMemcpyHostToDevice, 0));
-  }
-  if ((rc = gemm_fused_epilogue(da, db, static_cast<const float*>(dbias), static_cast<const float*>(dres),
-                                static_cast<float*>(dc), M, N, K, nullptr)) != FA_OK)
-    return rc;
-  FA_CUDA_TRY(cudaMemcpyAsync(C, dc, cb, cudaMemcpyDeviceToHost, 0));
-  FA_CUDA_TRY(cudaStreamSynchronize(0));
-  return FA_OK;
+  return host_pipe_drain(st);
 }
 
 int softmax_rows_host(const float* X, float* P, int rows, int N) {
@@ -525,14 +597,28 @@ int softmax_rows_host(const float* X, float* P, int rows, int N) {
   DeviceState* st = nullptr;
   int rc = current_device_state(&st);
   if (rc != FA_OK) return rc;
-  const size_t bytes = static_cast<size_t>(rows) * N * 4;
+  if ((rc = host_pipe_init(st)) != FA_OK) return rc;
+  const size_t pitch = static_cast<size_t>(N) * 4;
+  const size_t bytes = static_cast<size_t>(rows) * pitch;
   void* dx;
   if ((rc = scratch_get(st, 0, bytes, &dx)) != FA_OK) return rc;
-  FA_CUDA_TRY(cudaMemcpyAsync(dx, X, bytes, cudaMemcpyHostToDevice, 0));
-  if ((rc = softmax_rows(static_cast<const float*>(dx), static_cast<float*>(dx), rows, N, nullptr)) != FA_OK) return rc;
-  FA_CUDA_TRY(cudaMemcpyAsync(P, dx, bytes, cudaMemcpyDeviceToHost, 0));
-  FA_CUDA_TRY(cudaStreamSynchronize(0));
-  return FA_OK;
+  const int nchunk = host_chunks(2 * bytes, rows);
+  for (int c = 0; c < nchunk; ++c) {
+    const long long r0 = static_cast<long long>(rows) * c / nchunk, r1 = static_cast<long long>(rows) * (c + 1) / nchunk;
+    const size_t off = static_cast<size_t>(r0) * pitch, len = static_cast<size_t>(r1 - r0) * pitch;
+    float* const dchunk = reinterpret_cast<float*>(static_cast<char*>(dx) + off);
+    FA_CUDA_TRY(cudaMemcpyAsync(dchunk, reinterpret_cast<const char*>(X) + off, len, cudaMemcpyHostToDevice, st->s_in));
+    FA_CUDA_TRY(cudaEventRecord(st->ev_in[c], st->s_in));
+    FA_CUDA_TRY(cudaStreamWaitEvent(st->s_run, st->ev_in[c], 0));
+    if ((rc = softmax_rows(dchunk, dchunk, static_cast<int>(r1 - r0), N, st->s_run)) != FA_OK) {
+      host_pipe_drain(st);
+      return rc;
+    }
+    FA_CUDA_TRY(cudaEventRecord(st->ev_run[c], st->s_run));
+    FA_CUDA_TRY(cudaStreamWaitEvent(st->s_out, st->ev_run[c], 0));
+    FA_CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<char*>(P) + off, dchunk, len, cudaMemcpyDeviceToHost, st->s_out));
+  }
+  return host_pipe_drain(st);
 }
 
 int fa_host_release(void) {

@@ -87,3 +87,34 @@ def test_host_buffer_entry_points(fa, oracle):
     fa.softmax_rows_host(x, p)
     assert oracle.max_abs(p, oracle.softmax_rows(x)) <= 1e-6
     assert fa.launch_count() >= 5
+
+
+def test_host_buffer_calls_are_chunk_pipelined_and_identical_to_the_device_path(fa):
+    """Sizes large enough that the host-buffer entry points split the batch into several H2D / kernel / D2H chunks:
+    the result must be bit-identical to one device-resident call (chunks are independent units)."""
+    B, H, N, D = 2, 24, 2048, 128  # 25 MB per tensor -> several chunks; 48 (b,h) do not divide evenly by every count
+    g = torch.Generator().manual_seed(3)
+    q, k, v = ((torch.rand((B, H, N, D), generator=g) * 2 - 1).half().pin_memory() for _ in range(3))
+    out = torch.empty_like(q).pin_memory()
+    scale = D ** -0.5
+    fa.fa_forward_host(q, k, v, out, scale)
+    dev = fa.fa_forward(q.cuda(), k.cuda(), v.cuda(), scale)
+    torch.cuda.synchronize()
+    assert torch.equal(out, dev.cpu())
+    # second call reuses the cached scratch and streams
+    out2 = torch.empty_like(out)
+    fa.fa_forward_host(q, k, v, out2, scale)
+    assert torch.equal(out2, out)
+
+    a = (torch.rand((2000, 512), generator=g) * 2 - 1).half()
+    b = (torch.rand((512, 1536), generator=g) * 2 - 1).half()
+    bias, res = torch.rand((1536,), generator=g), torch.rand((2000, 1536), generator=g)
+    c = torch.empty((2000, 1536))
+    fa.gemm_fused_epilogue_host(a.numpy(), b.numpy(), bias.numpy(), res.numpy(), c.numpy())
+    cdev = fa.gemm_fused_epilogue(a.cuda(), b.cuda(), bias.cuda(), res.cuda())
+    assert torch.equal(c, cdev.cpu())
+
+    x = torch.randn((5000, 2048), generator=g) * 3
+    p = torch.empty_like(x)
+    fa.softmax_rows_host(x.numpy(), p.numpy())
+    assert torch.equal(p, fa.softmax_rows(x.cuda()).cpu())
