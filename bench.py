@@ -355,6 +355,24 @@ def reference_gpu_kernels(torch, dev):
     return out
 
 
+def graph_time_us(torch, f, calls=20, replays=10):
+    """GPU time per call with `calls` launches captured in ONE CUDA graph: what a launch-bound caller gets once the
+    host-side cost (ctypes, tensor-map encode, launch) is off the critical path."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        f()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(calls):
+            f()
+    g.replay()
+    torch.cuda.synchronize()
+    return time_loop(torch, g.replay, replays) / (replays * calls) * 1e3
+
+
 def extras(torch, fa, dev, peaks):
     """Companion entry points and the other single-GPU BASELINE configs (reported, not the headline)."""
     out = {}
@@ -366,15 +384,37 @@ def extras(torch, fa, dev, peaks):
     for _ in range(5):
         f()
     ms = time_loop(torch, f, 200) / 200
-    out["attn_cfg2_B4_H16_N1024_D64"] = {"us": ms * 1e3, "tflops": flops(B, H, N, D) / ms / 1e9}
+    gus = graph_time_us(torch, f)
+    out["attn_cfg2_B4_H16_N1024_D64"] = {"us": ms * 1e3, "tflops": flops(B, H, N, D) / ms / 1e9, "cuda_graph_us": gus,
+                                         "cuda_graph_tflops": flops(B, H, N, D) / gus / 1e6}
+    # the same shape through materialised scores (three launches) and its first stage alone
+    S = torch.empty((B * H, N, N), device=dev)
+    P = torch.empty((B * H, N, N), device=dev, dtype=torch.float16)
+    fu = lambda: fa.fa_forward_unfused(q, k, v, 0.125, workspace=(S, P))
+    fu()
+    out["attn_cfg2_unfused_3_launches"] = {"us": time_loop(torch, fu, 50) / 50 * 1e3}
+    fq = lambda: fa.gemm_batched(q.view(B * H, N, D), k.view(B * H, N, D), trans_b=True, alpha=0.125, out=S)
+    fq()
+    out["qk_scores_BH64_N1024_D64"] = {"us": time_loop(torch, fq, 50) / 50 * 1e3}
+    del S, P
     # config 1: latency only
     q1, k1, v1 = ((torch.rand((1, 1, 128, 64), device=dev) * 2 - 1).half() for _ in range(3))
     o1 = torch.empty_like(q1)
     f = lambda: fa.fa_forward(q1, k1, v1, 0.125, out=o1)
     for _ in range(5):
         f()
-    out["attn_cfg1_B1_H1_N128_D64"] = {"us": time_loop(torch, f, 200) / 200 * 1e3}
+    out["attn_cfg1_B1_H1_N128_D64"] = {"us": time_loop(torch, f, 200) / 200 * 1e3, "cuda_graph_us": graph_time_us(torch, f)}
     del q, k, v, o
+    # the reference's batched-GEMM shape: 8 x 512^3 (gemm_4_9_tensorcore_batched.cu:30-33)
+    ab = (torch.rand((8, 512, 512), device=dev) * 2 - 1).half()
+    bb = (torch.rand((8, 512, 512), device=dev) * 2 - 1).half()
+    cb = torch.empty((8, 512, 512), device=dev)
+    fb = lambda: fa.gemm_batched(ab, bb, out=cb)
+    fb()
+    gus = graph_time_us(torch, fb)
+    out["gemm_batched_8x512"] = {"us": time_loop(torch, fb, 100) / 100 * 1e3, "cuda_graph_us": gus,
+                                 "cuda_graph_tflops": 8 * 2.0 * 512 ** 3 / gus / 1e6}
+    del ab, bb, cb
     # config 5a: GEMM 8192^3 with fused epilogue
     M = Nn = K = 8192
     a = (torch.rand((M, K), device=dev) * 2 - 1).half()

@@ -10,7 +10,7 @@ def run(path):
     lib = ctypes.CDLL(path, mode=ctypes.RTLD_LOCAL)
     lib.fa_forward.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int] * 4 + [ctypes.c_float, ctypes.c_void_p]
     res = []
-    for (B, H, N, D, iters) in [(8, 32, 4096, 128, 30), (4, 16, 1024, 64, 200), (2, 8, 16384, 128, 10)]:
+    for (B, H, N, D, iters) in [(8, 32, 4096, 128, 30), (4, 16, 1024, 64, 200), (2, 8, 16384, 128, 10), (8, 32, 4096, 64, 20), (4, 37, 2048, 64, 50)]:
         g = torch.Generator(device="cuda").manual_seed(0)
         q, k, v = ((torch.rand((B, H, N, D), device="cuda", generator=g) * 2 - 1).half() for _ in range(3))
         o = torch.empty_like(q)

@@ -11,7 +11,7 @@ libname = sys.argv[2] if len(sys.argv) > 2 else "libfa_b200_trace.so"
 lib = ctypes.CDLL(os.path.join(ROOT, "flashattention_kernel_project_b200", libname))
 lib.fa_forward.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int] * 4 + [ctypes.c_float, ctypes.c_void_p]
 lib.fa_trace_config.argtypes = [ctypes.c_void_p, ctypes.c_int]
-B, H, N, D = 8, 32, 4096, 128
+B, H, N, D = 8, 32, 4096, int(os.environ.get("FA_TRACE_D", "128"))
 cta = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
 q, k, v = ((torch.rand((B, H, N, D), device="cuda") * 2 - 1).half() for _ in range(3))
 o = torch.empty_like(q)
