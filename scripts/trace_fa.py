@@ -11,7 +11,7 @@ libname = sys.argv[2] if len(sys.argv) > 2 else "libfa_b200_trace.so"
 lib = ctypes.CDLL(os.path.join(ROOT, "flashattention_kernel_project_b200", libname))
 lib.fa_forward.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int] * 4 + [ctypes.c_float, ctypes.c_void_p]
 lib.fa_trace_config.argtypes = [ctypes.c_void_p, ctypes.c_int]
-B, H, N, D = 8, 32, 4096, int(os.environ.get("FA_TRACE_D", "128"))
+B, H, N, D = 8, 32, int(os.environ.get("FA_TRACE_N", "4096")), int(os.environ.get("FA_TRACE_D", "128"))
 cta = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
 q, k, v = ((torch.rand((B, H, N, D), device="cuda") * 2 - 1).half() for _ in range(3))
 o = torch.empty_like(q)
@@ -43,6 +43,9 @@ for i in (0, 1):
     s_ready, ld, sd, c0, pa, mx = (col(i, k) for k in (1, 2, 3, 4, 5, 6))
     per = [b - a for a, b in zip(s_ready, s_ready[1:])]
     d = lambda x, y: st.mean(b - a for a, b in zip(x, y))
+    if os.environ.get("FA_TRACE_VERDICT"):
+        vw = col(i, 7)
+        print(f"soft{i}: held_compute={d(ld, mx):.0f} verdict_wait={d(mx, vw):.0f} after_verdict={d(vw, sd):.0f}")
     print(f"soft{i}: period={st.mean(per):.0f}  ld={d(s_ready, ld):.0f} max={d(ld, mx):.0f} stats={d(mx, sd):.0f} "
           f"chunk0={d(sd, c0):.0f} chunks1-3={d(c0, pa):.0f} wait_for_S={d(pa, s_ready[1:]):.0f}")
     p_seen, pv, qk = (col(4 + i, k) for k in (1, 3, 4))
