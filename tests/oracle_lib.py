@@ -334,6 +334,10 @@ class RefGpu:
         self.qk.ref_qk_launch.argtypes = [vp, vp, vp, c_int, c_int, c_int, c_float, vp]
         self.st16 = RefLib("streaming16").L
         self.st16.ref_streaming16_launch.argtypes = [vp, vp, vp, vp, c_int, c_int, c_float, vp]
+        self.sm_hybrid = RefLib("softmax_hybrid").L
+        self.sm_hybrid.ref_softmax_hybrid_launch.argtypes = [vp, vp, c_int, c_int, vp]
+        self.sm_warp = RefLib("softmax_warp").L
+        self.sm_warp.ref_softmax_warp_launch.argtypes = [vp, vp, c_int, c_int, vp]
 
     @staticmethod
     def _chk(rc, what):
@@ -386,3 +390,13 @@ class RefGpu:
         """q [B,16,16], kt [B,16,L] (transposed K), v [B,L,16] fp16 device tensors -> out fp32 [B,16,16]."""
         self._chk(self.st16.ref_streaming16_launch(q.data_ptr(), kt.data_ptr(), v.data_ptr(), out.data_ptr(), q.shape[0],
                                                    v.shape[1], float(scale), stream), "streaming16")
+
+    def softmax_block_hybrid(self, x, out, stream=0):
+        """fp32 [rows, N <= 512] device tensors (softmax_block_hybrid_kernel, `__expf`)."""
+        self._chk(self.sm_hybrid.ref_softmax_hybrid_launch(x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], stream),
+                  "softmax_block_hybrid")
+
+    def softmax_warp_shfl(self, x, out, stream=0):
+        """fp32 [rows, N <= 32] device tensors (softmax_warp_shfl_kernel)."""
+        self._chk(self.sm_warp.ref_softmax_warp_launch(x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], stream),
+                  "softmax_warp_shfl")

@@ -146,3 +146,21 @@ def test_softmax_against_the_reference_kernel_on_the_same_gpu(fa, oracle):
     RefGpu().softmax_naive(x, theirs)
     torch.cuda.synchronize()
     assert oracle.max_abs(ours.cpu().numpy(), theirs.cpu().numpy()) <= 1e-6
+
+
+@pytest.mark.skipif(not (ref_available("softmax_hybrid") and ref_available("softmax_warp")), reason="oracle/_ref not built")
+@pytest.mark.parametrize("rows,n,kind", [(4096, 512, "hybrid"), (1000, 384, "hybrid"), (333, 100, "hybrid"),
+                                         (4096, 32, "warp"), (1001, 17, "warp"), (64, 1, "warp")])
+def test_softmax_against_the_reference_sibling_kernels(fa, oracle, rows, n, kind):
+    """softmax_rows also stands in for softmax_block_hybrid_kernel (N <= 512, `__expf`;
+    Softmax micro kernel/softmax_block_hybrid/softmax_block_hybrid.cu:74-169) and softmax_warp_shfl_kernel (N <= 32;
+    ../softmax_warp_shfl_baseline/softmax_warp_shfl_baseline.cu:69-115): same buffers, both kernels."""
+    x = torch.randn((rows, n), device="cuda", generator=torch.Generator(device="cuda").manual_seed(rows + n)) * 3
+    ours = fa.softmax_rows(x)
+    theirs = torch.zeros_like(x)
+    r = RefGpu()
+    (r.softmax_block_hybrid if kind == "hybrid" else r.softmax_warp_shfl)(x, theirs)
+    torch.cuda.synchronize()
+    a, b = ours.cpu().numpy(), theirs.cpu().numpy()
+    assert oracle.max_abs(a, b) <= (2e-6 if kind == "hybrid" else 1e-6)  # `__expf` in the hybrid kernel: 2 ulp of exp
+    assert oracle.max_abs(a, oracle.softmax_rows(x.cpu().numpy())) <= 4e-6  # sequential vs tree row sums
