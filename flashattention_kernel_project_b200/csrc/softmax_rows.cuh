@@ -53,15 +53,32 @@ __global__ void __launch_bounds__(256) softmax_rows_reg_kernel(const float* X, T
   const int t = threadIdx.x % TPR;
   const int g = threadIdx.x / TPR;
   const int n4 = N >> 2;
-  for (long long row = static_cast<long long>(blockIdx.x) * kGroupsPerCta + g; row < rows;
-       row += static_cast<long long>(gridDim.x) * kGroupsPerCta) {
-    const float4* xin = reinterpret_cast<const float4*>(X + row * N);  // X == P allowed: a row is fully
-    TOut* pout = P + row * N;                                           // read before any of it is written
-    float4 v[V4];
+  const long long stride = static_cast<long long>(gridDim.x) * kGroupsPerCta;
+  const float4 kNegInf4 = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+  long long row = static_cast<long long>(blockIdx.x) * kGroupsPerCta + g;
+  // The next row of this thread group is already on its way from HBM while the current one is reduced and written:
+  // the two reductions (shuffles, and one shared-memory hop for a CTA-wide row) would otherwise leave the load queue empty.
+  float4 nxt[V4];
+  if (row < rows) {
+    const float4* xin = reinterpret_cast<const float4*>(X + row * N);
 #pragma unroll
     for (int i = 0; i < V4; ++i) {
       const int idx = i * TPR + t;
-      v[i] = (idx < n4) ? __ldcs(xin + idx) : make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+      nxt[i] = (idx < n4) ? __ldcs(xin + idx) : kNegInf4;
+    }
+  }
+  for (; row < rows; row += stride) {
+    TOut* pout = P + row * N;  // X == P allowed: a row is fully read before any of it is written (rows are disjoint)
+    float4 v[V4];
+#pragma unroll
+    for (int i = 0; i < V4; ++i) v[i] = nxt[i];
+    if (row + stride < rows) {
+      const float4* xin = reinterpret_cast<const float4*>(X + (row + stride) * N);
+#pragma unroll
+      for (int i = 0; i < V4; ++i) {
+        const int idx = i * TPR + t;
+        nxt[i] = (idx < n4) ? __ldcs(xin + idx) : kNegInf4;
+      }
     }
     float m = -CUDART_INF_F;
 #pragma unroll
