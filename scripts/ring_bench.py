@@ -20,16 +20,22 @@ g = torch.Generator(device=dev).manual_seed(7 + rank)
 q, k, v = ((torch.rand((B, H, n, D), device=dev, generator=g) * 2 - 1).half() for _ in range(3))
 scale = D ** -0.5
 comm = torch.cuda.Stream(device=dev)
-ring = fa.new_ring_group()
+mode = os.environ.get("RING_MODE", "nccl")  # pull: CUDA IPC peer mappings + copy engines; nccl: send/recv rank -> rank+1
+if mode == "pull":
+    peers = fa.PeerShards(k, v)
+    run = lambda: fa.ring_attention_pull(q, peers, scale, copy_stream=comm)
+else:
+    ring = fa.new_ring_group()
+    run = lambda: fa.ring_attention(q, k, v, scale, group=ring, comm_stream=comm)
 for _ in range(2):
-    out = fa.ring_attention(q, k, v, scale, group=ring, comm_stream=comm)
+    out = run()
 dist.barrier()
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 iters = 3
 e0.record()
 for _ in range(iters):
-    out = fa.ring_attention(q, k, v, scale, group=ring, comm_stream=comm)
+    out = run()
 e1.record()
 torch.cuda.synchronize()
 ms = torch.tensor([e0.elapsed_time(e1) / iters], device=dev, dtype=torch.float64)
@@ -49,7 +55,9 @@ torch.cuda.synchronize()
 ms_c = e0.elapsed_time(e1) / iters
 if rank == 0:
     fl = 4.0 * B * H * N * N * D
-    print(json.dumps({"config": "attention fwd B=1,H=32,N=65536,D=128 ring/context-parallel", "n_gpus": world,
+    print(json.dumps({"config": "attention fwd B=1,H=32,N=65536,D=128 ring/context-parallel", "exchange": mode, "n_gpus": world,
                       "ms": float(ms.item()), "tflops_total": fl / float(ms.item()) / 1e9,
                       "ms_compute_only_rank0": ms_c, "exchange_bytes_per_gpu_per_step": 2 * B * H * n * D * 2}))
+if mode == "pull":
+    peers.close()
 dist.destroy_process_group()

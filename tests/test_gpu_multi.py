@@ -1,5 +1,6 @@
 """Multi-GPU GPU tests (skipped on a single-GPU box; run with `gpurun --gpus 2`): (b,h) sharding with no
-collective, and the ring / context-parallel path with NCCL send/recv + fa_forward_partial."""
+collective, and the ring / context-parallel path with fa_forward_partial -- K/V passed along with NCCL send/recv, and
+pulled from their owners through CUDA IPC peer mappings."""
 import os
 import socket
 
@@ -38,9 +39,18 @@ def _worker(rank, world, port, mode, q, k, v, scale, out_path):
         else:
             n = N // world
             sl = slice(rank * n, (rank + 1) * n)
-            out = fa.ring_attention(q[:, :, sl].contiguous().cuda(), k[:, :, sl].contiguous().cuda(),
-                                    v[:, :, sl].contiguous().cuda(), scale, group=fa.new_ring_group())
+            qs, ks, vs = (x[:, :, sl].contiguous().cuda() for x in (q, k, v))
+            out = fa.ring_attention(qs, ks, vs, scale, group=fa.new_ring_group())
             torch.cuda.synchronize()
+            if mode == "pull":
+                # the same ring with every K/V shard peer-mapped and pulled from its owner by the copy engines:
+                # same visiting order, same kernel calls -> bit-identical to the NCCL exchange
+                peers = fa.PeerShards(ks, vs)
+                pulled = fa.ring_attention_pull(qs, peers, scale)
+                again = fa.ring_attention_pull(qs, peers, scale)  # buffers and mappings are reusable
+                peers.close()
+                assert torch.equal(pulled, out) and torch.equal(again, out)
+                out = pulled
             gathered = [torch.empty_like(out) for _ in range(world)]
             dist.all_gather(gathered, out)  # test-only
             full = torch.cat(gathered, dim=2)
@@ -51,7 +61,8 @@ def _worker(rank, world, port, mode, q, k, v, scale, out_path):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
-@pytest.mark.parametrize("mode,shape", [("bh", (2, 5, 640, 128)), ("ring", (1, 4, 1024, 128)), ("ring", (2, 2, 768, 64))])
+@pytest.mark.parametrize("mode,shape", [("bh", (2, 5, 640, 128)), ("ring", (1, 4, 1024, 128)), ("ring", (2, 2, 768, 64)),
+                                        ("pull", (1, 4, 1024, 128)), ("pull", (2, 3, 512, 64))])
 def test_two_gpu_paths_match_oracle(tmp_path, oracle, mode, shape):
     B, H, N, D = shape
     rng = np.random.default_rng(5)
