@@ -73,6 +73,7 @@ struct DeviceState {
   void* scratch[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   size_t scratch_bytes[6] = {0, 0, 0, 0, 0, 0};
   // the *_host entry points pipeline H2D copy / kernel / D2H copy over chunks of the batch on three streams
+  std::mutex host_mu;  // one *_host call at a time per device: they share the scratch buffers and the three streams
   bool pipe_ready = false;
   cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
   cudaEvent_t ev_in[16], ev_run[16];
@@ -511,6 +512,7 @@ int fa_forward_host(const void* Q, const void* K, const void* V, void* O, int B,
   DeviceState* st = nullptr;
   int rc = current_device_state(&st);
   if (rc != FA_OK) return rc;
+  std::lock_guard<std::mutex> host_lock(st->host_mu);
   if ((rc = host_pipe_init(st)) != FA_OK) return rc;
   const size_t unit = static_cast<size_t>(N) * D * 2;  // bytes of one (b,h) of one tensor
   const size_t bytes = static_cast<size_t>(bh) * unit;
@@ -549,6 +551,7 @@ int gemm_fused_epilogue_host(const void* A, const void* Bm, const float* bias, c
   DeviceState* st = nullptr;
   int rc = current_device_state(&st);
   if (rc != FA_OK) return rc;
+  std::lock_guard<std::mutex> host_lock(st->host_mu);
   if ((rc = host_pipe_init(st)) != FA_OK) return rc;
   const size_t ab = static_cast<size_t>(M) * K * 2, bb = static_cast<size_t>(K) * N * 2;
   const size_t cb = static_cast<size_t>(M) * N * 4, biasb = static_cast<size_t>(N) * 4;
@@ -597,6 +600,7 @@ int softmax_rows_host(const float* X, float* P, int rows, int N) {
   DeviceState* st = nullptr;
   int rc = current_device_state(&st);
   if (rc != FA_OK) return rc;
+  std::lock_guard<std::mutex> host_lock(st->host_mu);
   if ((rc = host_pipe_init(st)) != FA_OK) return rc;
   const size_t pitch = static_cast<size_t>(N) * 4;
   const size_t bytes = static_cast<size_t>(rows) * pitch;
@@ -628,6 +632,7 @@ int fa_host_release(void) {
     return FA_ERR_NO_DEVICE;
   }
   DeviceState& st = g_dev[dev];
+  std::lock_guard<std::mutex> host_lock(st.host_mu);
   for (int i = 0; i < 6; ++i) {
     if (st.scratch[i] != nullptr) cudaFree(st.scratch[i]);
     st.scratch[i] = nullptr;

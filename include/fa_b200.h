@@ -140,7 +140,9 @@ int fa_forward_unfused(const void* Q, const void* K, const void* V, float* O, fl
  * e.g. flashattn_streaming_16x32_2warp_softmax_v12i.cu:325-368) behind one call.  All pointers
  * are HOST pointers (pinned memory makes the copies asynchronous); device scratch is cached
  * inside the library per device and grown on demand.  The call returns after the result is in
- * the host buffer.  fa_host_release() frees the cached scratch of the current device.
+ * the host buffer.  The batch is cut into up to 16 chunks of independent units whose H2D copy, kernel and D2H
+ * copy overlap on three internal streams.  Calls on one device are serialised (they share the scratch);
+ * calls on different devices run concurrently.  fa_host_release() frees the cached scratch of the current device.
  */
 int fa_forward_host(const void* Q, const void* K, const void* V, void* O, int B, int H, int N, int D,
                     float scale);

@@ -88,3 +88,30 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.lower() or f == "__init__.py" and "oracle" not in text, (dirpath, f)
+
+
+def build_and_run_c_example(tmp_path):
+    """gcc-compiles examples/drop_in.c against include/fa_b200.h + libfa_b200.so and runs it."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cc = shutil.which("gcc")
+    if cc is None:
+        pytest.skip("gcc not available")
+    subprocess.run([cc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c",
+                    os.path.join(root, "include", "fa_b200.h")], check=True)
+    libdir = os.path.join(root, "flashattention_kernel_project_b200")
+    exe = str(tmp_path / "drop_in")
+    subprocess.run([cc, "-std=c99", "-Wall", "-I" + os.path.join(root, "include"), os.path.join(root, "examples", "drop_in.c"),
+                    "-o", exe, "-L" + libdir, "-lfa_b200", "-lm", "-Wl,-rpath," + libdir], check=True)
+    return subprocess.run([exe], capture_output=True, text=True, timeout=120)
+
+
+def test_header_is_plain_c_and_a_c_program_links_against_the_library(tmp_path):
+    """The boundary is C, not C++: the header compiles as C99 with -pedantic, and examples/drop_in.c (gcc, no CUDA
+    headers) links against libfa_b200.so.  Without an sm_100 GPU the program must report FA_ERR_NO_DEVICE (exit 2);
+    tests/test_gpu_ring_host.py runs the same program on the GPU box, where it checks an output row itself."""
+    r = build_and_run_c_example(tmp_path)
+    assert "fa_version" in r.stdout
+    if not torch.cuda.is_available():
+        assert r.returncode == 2 and "-5" in r.stdout, r.stdout  # FA_ERR_NO_DEVICE, reported through fa_strerror

@@ -118,3 +118,11 @@ def test_host_buffer_calls_are_chunk_pipelined_and_identical_to_the_device_path(
     p = torch.empty_like(x)
     fa.softmax_rows_host(x.numpy(), p.numpy())
     assert torch.equal(p, fa.softmax_rows(x.cuda()).cpu())
+
+
+def test_plain_c_program_through_the_c_abi(tmp_path):
+    """examples/drop_in.c: a gcc-built C99 program (no CUDA headers, no Python) calls fa_forward_host and checks a row."""
+    from tests.test_abi import build_and_run_c_example
+    r = build_and_run_c_example(tmp_path)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "max abs error" in r.stdout
