@@ -141,3 +141,13 @@ def test_rejected_calls(fa):
     with pytest.raises(FaError) as e:  # N % 8 != 0: row pitch of C is not a multiple of 16 B
         fa.gemm_batched(a, torch.zeros((2, 16, 12), dtype=torch.float16, device="cuda"))
     assert e.value.code == -3
+
+
+def test_many_tiny_batch_entries(fa, oracle):
+    """4096 entries of 16 x 24 x 16: one 256 x 256 output tile per entry, 4096 tiles walked by 74 persistent CTA pairs."""
+    a, b = _rand_half((4096, 16, 16), 21), _rand_half((4096, 16, 24), 22)
+    got = _run(fa, a, b)
+    ref = np.einsum("zmk,zkn->zmn", a.astype(np.float32), b.astype(np.float32))
+    assert oracle.max_abs(got, ref) <= TOL_ABS and oracle.rel_l2(got, ref) <= TOL_REL
+    sel = [0, 73, 74, 2047, 4095]
+    assert oracle.max_abs(got[sel], oracle.gemm_batched(a[sel].astype(np.float32), b[sel].astype(np.float32))) <= TOL_ABS

@@ -164,3 +164,19 @@ def test_softmax_against_the_reference_sibling_kernels(fa, oracle, rows, n, kind
     a, b = ours.cpu().numpy(), theirs.cpu().numpy()
     assert oracle.max_abs(a, b) <= (2e-6 if kind == "hybrid" else 1e-6)  # `__expf` in the hybrid kernel: 2 ulp of exp
     assert oracle.max_abs(a, oracle.softmax_rows(x.cpu().numpy())) <= 4e-6  # sequential vs tree row sums
+
+
+def test_gemm_residual_in_place(fa, oracle):
+    """C may alias the residual, as in the reference kernel (read residual[idx], then write C[idx],
+    tensorcore_gemm_fused_epilogue.cu:119-126): the epilogue reads a block's residual before it stores that block."""
+    M, N, K = 1000, 1096, 264
+    a, b, bias, res = _gemm_inputs(M, N, K, seed=77)
+    ref = oracle.gemm_fused_f16(a, b, bias, res)
+    c = torch.from_numpy(res.copy()).cuda()
+    out = fa.gemm_fused_epilogue(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(), torch.from_numpy(bias).cuda(), c, out=c)
+    torch.cuda.synchronize()
+    assert out.data_ptr() == c.data_ptr()
+    got = c.cpu().numpy()
+    assert oracle.max_abs(got, ref) <= 2e-3 and oracle.rel_l2(got, ref) <= 1e-3
+    separate = _gemm(fa, a, b, bias, res)
+    assert np.array_equal(got, separate)
