@@ -69,7 +69,7 @@ struct FaCfg {
   static constexpr int kOffFac = kOffKV + kStages * kTileBytes;  // float[2][128] rescale factors / final m
   static constexpr int kOffSum = kOffFac + 2 * 128 * 4;          // float[2][128] final l
   static constexpr int kOffBar = kOffSum + 2 * 128 * 4;
-  static constexpr int kPChunks = 2;                    // P is published in two chunks: keys [0,96), [96,128)
+  static constexpr int kPChunks = 2;                    // P is published in two chunks: keys [0, 16*kSplitGroups), then the rest
   static constexpr int kNumBars = 2 + 2 * kStages + 8 + 2 * kPChunks;
   static constexpr int kOffTmem = kOffBar + kNumBars * 8;
   static constexpr int kSmemBytes = kOffTmem + 16;
@@ -92,16 +92,18 @@ constexpr float kLazyRescaleTau = 8.0f;  // log2 units: P stays below 2^8, far i
 // not pay yet; it is kept as a build-time knob for the schedules of later rounds.
 constexpr int kPolyPer8 = FA_POLY_PER8;
 
-// Schedule knobs (build-time; defaults are the measured best on B200)
+// Schedule knobs (build-time; defaults are the measured best on B200, see DESIGN.md 3.1: period per 128 keys and tile
+// from the clock64 trace, config 3 -- head 0/8/12/16/20/24/32/48/64 keys x split 2..7 groups: 16 x 4 -> 3234 cycles,
+// 32 x 6 (the first shipped setting) -> 3356, 64 x 4 -> 4711)
 #ifndef FA_SPEC_KEYS
-#define FA_SPEC_KEYS 32   // exps computed against the stale max in the shadow of the row-max chain
+#define FA_SPEC_KEYS 16   // exps computed against the stale max in the shadow of the row-max chain
 #endif
 #ifndef FA_SPLIT_GROUPS
-#define FA_SPLIT_GROUPS 6  // P is published after this many 16-key groups, then after all 8
+#define FA_SPLIT_GROUPS 4  // P is published after this many 16-key groups, then after all 8
 #endif
 constexpr int kSpecKeys = FA_SPEC_KEYS;
 constexpr int kSplitGroups = FA_SPLIT_GROUPS;
-static_assert(kSpecKeys % 16 == 0 && kSpecKeys >= 16 && kSpecKeys <= 64, "speculative head is whole 16-key groups");
+static_assert(kSpecKeys % 4 == 0 && kSpecKeys >= 0 && kSpecKeys <= 64, "speculative head is whole key quads");
 static_assert(kSplitGroups >= 1 && kSplitGroups <= 7, "first publication covers 1..7 groups of 16 keys");
 
 // Developer timeline trace (scripts/trace_fa.py builds a separate library with -DFA_TRACE): CTA
@@ -221,14 +223,14 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
           for (int k = 0; k < 128; ++k)
             if (k >= valid) s[k] = -INFINITY;
         }
-        // ---- speculative head: the exps of the first 32 keys are computed against the STALE running
+        // ---- speculative head: the exps of the first kSpecKeys keys are computed against the STALE running
         // max while the 64-instruction row-max chain runs in their shadow (MUFU and ALU pipes overlap).
         // The lazy-rescale rule makes the stale max the common case; when a row does need a new max
-        // (always at j == 0, where the stale max is -inf) its 32 exps are simply redone.
+        // (always at j == 0, where the stale max is -inf) those exps are simply redone.
         const uint64_t c2 = pack_f32x2(c, c);
         float neg_mc = -m_used * c;
         uint64_t neg_mc2 = pack_f32x2(neg_mc, neg_mc);
-        float pe[kSpecKeys];
+        float pe[kSpecKeys > 0 ? kSpecKeys : 4];
 #pragma unroll
         for (int k = 0; k < kSpecKeys; k += 2) {
           float x0, x1;
@@ -285,7 +287,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
         if ((warp & 3) == 0 && lane == 0) FA_TRACE_POINT(i, j, 3);
 
         // ---- exps, packed row sums, fp16 P written back over S; P is published to the MMA warp in two
-        // chunks (keys [0,96) then [96,128)) so most PV MMAs overlap the tail of the softmax
+        // chunks (keys [0,64) then [64,128)) so half of the PV MMAs overlap the tail of the softmax
         uint64_t lsum_a = pack_f32x2(0.f, 0.f), lsum_b = pack_f32x2(0.f, 0.f);
         const float cy = c * (1.f / 128.f);                 // y = sat(s*cy + by) encodes x = 128*y - 120
         const float by = (neg_mc + 120.f) * (1.f / 128.f);
