@@ -215,6 +215,12 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # Burst figure first, while the part is still cool: 3 + 20 launches (~45 ms) finish before the power cap pulls the
+    # clock down.  Reported next to the sustained number below, against the burst cuBLAS peak.
+    for _ in range(3):
+        step()
+    barrier()
+    burst_ms = time_loop(torch, step, 20) / 20
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
@@ -264,6 +270,13 @@ def run_ours(args):
     peaks, peak_src = load_peaks()
     kernel_ms = ms_total / args.steps  # rank 0's own average launch duration (back-to-back launches, one kernel per step)
     achieved = per_gpu_flops / (kernel_ms * 1e-3) / 1e12
+    burst = per_gpu_flops / (burst_ms * 1e-3) / 1e12
+    # The denominator follows how the kernel was timed: inside a long back-to-back run the part sits at its power cap,
+    # so the comparable cuBLAS figure is the sustained one; a short timed region compares with the burst figure.
+    long_run = ms_total >= 250.0 and "bf16_tflops_sustained" in peaks
+    peak = peaks["bf16_tflops_sustained"] if long_run else peaks["bf16_tflops"]
+    peak_kind = ("sustained cuBLAS bf16 (kernel timed inside a %.0f ms back-to-back run)" % ms_total) if long_run \
+        else "burst cuBLAS bf16 (timed region %.0f ms)" % ms_total
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "fa_fwd_traffic.json")
     if os.path.exists(tpath):
@@ -283,9 +296,11 @@ def run_ours(args):
                 "d2h_bytes_per_step": tensor_bytes, "steps": e2e_steps, "api": "fa_forward_host (C ABI, pinned host buffers)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "fa_fwd_kernel<128>", "achieved": achieved,
-                     "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
-                     "peak_source": peak_src + ", burst cuBLAS bf16",
-                     "frac_of_sustained": achieved / peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]),
+                     "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                     "peak_source": peak_src + ", " + peak_kind,
+                     "achieved_burst": burst, "frac_burst_of_burst_peak": burst / peaks["bf16_tflops"],
+                     "frac_of_burst_peak": achieved / peaks["bf16_tflops"],
+                     "frac_of_sustained_peak": achieved / peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]),
                      "frac_of_nominal_2250": achieved / NOMINAL_TFLOPS,
                      "algorithmic_flops_per_launch": per_gpu_flops, "traffic": traffic},
     }
