@@ -83,14 +83,15 @@ enum : uint32_t {
 };
 
 constexpr float kLazyRescaleTau = 8.0f;  // log2 units: P stays below 2^8, far inside fp16 range
-#ifndef FA_POLY_PER8
-#define FA_POLY_PER8 0
+#ifndef FA_POLY_MASK
+#define FA_POLY_MASK 0x11
 #endif
-// Of every 8 keys (outside the speculative head) this many take the FMA-pipe polynomial exp2 instead of the
-// MUFU.  Measured on B200 (config 3): 0 -> 1210, 2 -> 1218, 4 -> 1150 TFLOP/s -- with one softmax warp per SM
-// sub-partition and tile, a warp's own MUFU issue stall and its FMA work do not overlap, so the offload does
-// not pay yet; it is kept as a build-time knob for the schedules of later rounds.
-constexpr int kPolyPer8 = FA_POLY_PER8;
+// Which of the 8 key PAIRS of a 16-key group take the FMA-pipe polynomial exp2 instead of MUFU.EX2 (bit i = pair i;
+// pairs inside the speculative head always use the MUFU).  Measured on B200, config 3, interleaved 2 s blocks at the
+// power cap (scripts/sustained_ab.py, +-0.2 %): 0x00 -> 1020, 0x11 (25 %) -> 1050, 0x55 (50 %) -> 1025 TFLOP/s.  In
+// short bursts the MUFU-only build is as fast or faster (a warp's MUFU stall and its FMA work do not overlap), but a
+// launch then costs more energy, and the sustained rate is set by energy per launch.
+constexpr unsigned kPolyMask = FA_POLY_MASK;
 
 // Schedule knobs (build-time; defaults are the measured best on B200, see DESIGN.md 3.1: period per 128 keys and tile
 // from the clock64 trace, config 3 -- head 0/8/12/16/20/24/32/48/64 keys x split 2..7 groups: 16 x 4 -> 3234 cycles,
@@ -301,15 +302,14 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
             if (e < kSpecKeys) {
               p0 = pe[e]; p1 = pe[e + 1]; p2 = pe[e + 2]; p3 = pe[e + 3];
             } else {
-              // of every 8 keys, kPolyPer8 take the FMA-pipe polynomial and the rest the MUFU
               float x0, x1, x2, x3;
-              if ((k & 7) < kPolyPer8) {
+              if ((kPolyMask >> (k / 2)) & 1u) {
                 exp2_poly_pair(pack_f32x2(ffma_sat(s[e + 0], cy, by), ffma_sat(s[e + 1], cy, by)), p0, p1);
               } else {
                 unpack_f32x2(ffma2(pack_f32x2(s[e + 0], s[e + 1]), c2, neg_mc2), x0, x1);
                 p0 = ex2_approx(x0); p1 = ex2_approx(x1);
               }
-              if (((k + 2) & 7) < kPolyPer8) {
+              if ((kPolyMask >> (k / 2 + 1)) & 1u) {
                 exp2_poly_pair(pack_f32x2(ffma_sat(s[e + 2], cy, by), ffma_sat(s[e + 3], cy, by)), p2, p3);
               } else {
                 unpack_f32x2(ffma2(pack_f32x2(s[e + 2], s[e + 3]), c2, neg_mc2), x2, x3);
