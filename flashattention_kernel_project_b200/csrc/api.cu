@@ -8,6 +8,7 @@
 // every failure is a return code.
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -76,9 +77,9 @@ struct DeviceState {
   std::mutex host_mu;  // one *_host call at a time per device: they share the scratch buffers and the three streams
   bool pipe_ready = false;
   cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
-  cudaEvent_t ev_in[16], ev_run[16];
+  cudaEvent_t ev_in[64], ev_run[64];
 };
-constexpr int kHostChunksMax = 16;
+constexpr int kHostChunksMax = 64;  // events allocated per device; the chunk count actually used is host_chunk_limit()
 DeviceState g_dev[kMaxDevices];
 std::mutex g_mutex;
 unsigned int* g_dbg_host = nullptr;  // mapped pinned page shared by all devices
@@ -394,10 +395,19 @@ int host_pipe_drain(DeviceState* st) {
   if (b != cudaSuccess) return static_cast<int>(b);
   return c == cudaSuccess ? FA_OK : static_cast<int>(c);
 }
-// Chunks of >= 8 MB of traffic each, at most kHostChunksMax and at most one per unit.
+// Upper bound on the chunks of one *_host call: 16 unless FA_HOST_CHUNKS (1..64) says otherwise.
+int host_chunk_limit() {
+  static const int limit = [] {
+    const char* e = std::getenv("FA_HOST_CHUNKS");
+    const int v = e != nullptr ? std::atoi(e) : 0;
+    return (v >= 1 && v <= kHostChunksMax) ? v : 16;
+  }();
+  return limit;
+}
+// Chunks of >= 8 MB of traffic each, at most host_chunk_limit() and at most one per unit.
 int host_chunks(size_t total_bytes, long long units) {
   long long n = static_cast<long long>(total_bytes >> 23);
-  if (n > kHostChunksMax) n = kHostChunksMax;
+  if (n > host_chunk_limit()) n = host_chunk_limit();
   if (n > units) n = units;
   return n < 1 ? 1 : static_cast<int>(n);
 }
