@@ -24,7 +24,7 @@ for r in rows[1:]:
     except ValueError:
         pass
 tot = sum(sum(v) for v in d.values())
-lines = [f"# ncu launch list ({tag}): `ncu --metrics gpu__time_duration.sum --clock-control none` around `python bench.py --steps 5 --warmup 3 --no-cpu --no-extras` (5 + 3 config-3 launches, then the chunk-pipelined e2e leg: 16 (b,h) chunks per step)",
+lines = [f"# ncu launch list ({tag}): `ncu --metrics gpu__time_duration.sum --clock-control none` around `python bench.py --steps 5 --warmup 3 --no-cpu --no-extras` (burst probe 3 + 20, warm-up 3, timed 5 config-3 launches; then the chunk-pipelined e2e leg: 16 (b,h)-chunk launches per host step)",
          "# per-launch times are cold-cache and serialised: compare SHARES, not absolutes", "",
          f"{'kernel':70s} {'launches':>8s} {'total_us':>10s} {'avg_us':>9s} {'share':>6s}"]
 for k, v in sorted(d.items(), key=lambda kv: -sum(kv[1])):
