@@ -1,6 +1,7 @@
-// C = ReLU(A*B + bias[col]) + residual on sm_100a: persistent CTA PAIRS (cluster of 2), TMA A/B ring ->
+// C = act(alpha * A*op(B) + bias[col]) + residual on sm_100a: persistent CTA PAIRS (cluster of 2), TMA A/B ring ->
 // tcgen05.mma.cta_group::2 256x256x16 -> double-buffered fp32 accumulators in TMEM -> tcgen05.ld ->
-// fused epilogue -> global.
+// epilogue combined in shared memory with TMA-fetched residual blocks -> TMA store.  Batched (third TMA coordinate),
+// B either [K,N] (MN-major operand) or [N,K] (K-major operand, C = A*B^T).
 //
 // Replaces wmma_gemm_fused_kernel (GEMM/tensorcore_gemm_fused_epilogue/tensorcore_gemm_fused_epilogue.cu:53-130):
 // one warp per 16x16 C tile, WMMA fragments loaded straight from global every k-step (:80-88),
