@@ -442,7 +442,13 @@ def extras(torch, fa, dev, peaks):
         f()
     ms = time_loop(torch, f, 20) / 20
     tf = 2.0 * M * Nn * K / ms / 1e9
-    out["gemm_fused_8192"] = {"ms": ms, "tflops": tf, "frac_of_measured_peak": tf / peaks["bf16_tflops"]}
+    # the same kernel held at the power cap: ~1.2 s of back-to-back launches, last 0.8 s timed
+    time_loop(torch, f, 500)
+    ms_s = time_loop(torch, f, 1000) / 1000
+    tf_s = 2.0 * M * Nn * K / ms_s / 1e9
+    out["gemm_fused_8192"] = {"ms": ms, "tflops": tf, "frac_of_measured_peak": tf / peaks["bf16_tflops"],
+                              "timing": "20 launches (burst)", "sustained_tflops": tf_s,
+                              "sustained_frac_of_measured_sustained_peak": tf_s / peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])}
     del a, b, res, c
     # config 5b: softmax 16384 x 4096
     x = torch.randn((16384, 4096), device=dev)
