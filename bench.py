@@ -340,6 +340,11 @@ def reference_gpu_kernels(torch, dev):
     out["v12i_native_B1024_M16_L128_D16"] = {
         "reference_us": timeit(lambda: ref.v12i_kernel(q16, k16, v16, o16, 0.25), 200) * 1e3,
         "ours_us": timeit(lambda: fa.fa_forward_cross(q16[None], k16[None], v16[None], 0.25, out=o16[None]), 200) * 1e3}
+    if ref_available("mw_v10") and ref_available("mw_v11"):  # the true-WMMA streaming kernels, same native shape
+        entry = {"ours_us": out["v12i_native_B1024_M16_L128_D16"]["ours_us"]}
+        for ver in ("v10", "v11"):
+            entry[f"reference_{ver}_us"] = timeit(lambda: ref.streaming_mw(ver, q16, k16, v16, o16, 0.25), 200) * 1e3
+        out["streaming_mw_v10_v11_native_B1024_M16_L128_D16"] = entry
     q1, o1 = q16[:, 0].contiguous(), torch.zeros((1024, 16), device=dev)
     out["v7_5_native_B1024_S128_D16_single_query"] = {
         "reference_us": timeit(lambda: ref.v7_5_kernel(q1, k16, v16, o1), 200) * 1e3,

@@ -334,6 +334,11 @@ class RefGpu:
         self.qk.ref_qk_launch.argtypes = [vp, vp, vp, c_int, c_int, c_int, c_float, vp]
         self.st16 = RefLib("streaming16").L
         self.st16.ref_streaming16_launch.argtypes = [vp, vp, vp, vp, c_int, c_int, c_float, vp]
+        self.mw = {}
+        for ver in ("v10", "v11"):
+            L = RefLib("mw_" + ver).L
+            getattr(L, f"ref_mw_{ver}_launch").argtypes = [vp, vp, vp, vp, c_int, c_int, c_float, vp]
+            self.mw[ver] = getattr(L, f"ref_mw_{ver}_launch")
         self.sm_hybrid = RefLib("softmax_hybrid").L
         self.sm_hybrid.ref_softmax_hybrid_launch.argtypes = [vp, vp, c_int, c_int, vp]
         self.sm_warp = RefLib("softmax_warp").L
@@ -400,3 +405,9 @@ class RefGpu:
         """fp32 [rows, N <= 32] device tensors (softmax_warp_shfl_kernel)."""
         self._chk(self.sm_warp.ref_softmax_warp_launch(x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], stream),
                   "softmax_warp_shfl")
+
+    def streaming_mw(self, ver, q, k, v, out, scale, stream=0):
+        """flashattn_streaming_16x16_kernel_mw_v10 / _v11: q [B,16,16], k [B,L,16] (row per key), v [B,L,16] fp16 device
+        tensors -> out fp32 [B,16,16]."""
+        self._chk(self.mw[ver](q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), q.shape[0], k.shape[1],
+                               float(scale), stream), "mw_" + ver)

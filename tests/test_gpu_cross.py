@@ -76,3 +76,27 @@ def test_cross_rejects_unsupported_head_dim(fa):
     with pytest.raises(fa.FaError) as e:
         fa.fa_forward_cross(q, q, q, 0.1)
     assert e.value.code == -2
+
+
+@pytest.mark.skipif(not (ref_available("mw_v10") and ref_available("mw_v11")), reason="oracle/_ref not built")
+@pytest.mark.parametrize("ver", ["v10", "v11"])
+def test_against_the_wmma_streaming_kernels_v10_v11_at_their_native_shape(fa, oracle, ver):
+    """SURVEY 8(a) a4: flashattn_streaming_16x16_kernel_mw_v10 / _v11 (QK^T on WMMA, two warps, cp.async ping-pong;
+    flashattn_warp_spc/flashattn_streaming_16x16_mw_v10.cu:104-281, ..._v11.cu:101-283) at B = 1024, M = 16, L = 128,
+    D = 16, normal(0,1) inputs as in their harness, run on the same buffers as fa_forward_cross; both against the
+    streaming family's host oracle (`+1e-6` normaliser)."""
+    B, L = 1024, 128
+    rng = np.random.default_rng(42)
+    q = rng.standard_normal((B, 16, 16)).astype(np.float16)
+    k = rng.standard_normal((B, L, 16)).astype(np.float16)   # row per key = the kernels' K_T
+    v = rng.standard_normal((B, L, 16)).astype(np.float16)
+    tq, tk, tv = (torch.from_numpy(x).cuda() for x in (q, k, v))
+    theirs = torch.zeros((B, 16, 16), device="cuda")
+    RefGpu().streaming_mw(ver, tq, tk, tv, theirs, 0.25)
+    ours = fa.fa_forward_cross(tq[None], tk[None], tv[None], 0.25)
+    torch.cuda.synchronize()
+    ref = oracle.streaming_ref_f16(q, np.ascontiguousarray(k.transpose(0, 2, 1)), v, 0.25)
+    a, b = ours[0].cpu().numpy(), theirs.cpu().numpy()
+    assert oracle.max_abs(a, ref) <= 2e-3 and oracle.rel_l2(a, ref) <= 1e-3
+    assert oracle.max_abs(b, ref) <= 2e-3 and oracle.rel_l2(b, ref) <= 1e-3
+    assert oracle.max_abs(a, b) <= 2e-3 and oracle.rel_l2(a, b) <= 1e-3
