@@ -341,10 +341,14 @@ def reference_gpu_kernels(torch, dev):
         "reference_us": timeit(lambda: ref.v12i_kernel(q16, k16, v16, o16, 0.25), 200) * 1e3,
         "ours_us": timeit(lambda: fa.fa_forward_cross(q16[None], k16[None], v16[None], 0.25, out=o16[None]), 200) * 1e3}
     if ref_available("mw_v10") and ref_available("mw_v11"):  # the true-WMMA streaming kernels, same native shape
-        entry = {"ours_us": out["v12i_native_B1024_M16_L128_D16"]["ours_us"]}
+        # GPU time per launch with 20 launches captured in one CUDA graph (these kernels are shorter than a Python call)
+        s_cur = lambda: torch.cuda.current_stream().cuda_stream
+        entry = {"ours_cuda_graph_us": graph_time_us(torch, lambda: fa.fa_forward_cross(q16[None], k16[None], v16[None], 0.25, out=o16[None])),
+                 "reference_v12i_cuda_graph_us": graph_time_us(torch, lambda: ref.v12i_kernel(q16, k16, v16, o16, 0.25, stream=s_cur()))}
         for ver in ("v10", "v11"):
-            entry[f"reference_{ver}_us"] = timeit(lambda: ref.streaming_mw(ver, q16, k16, v16, o16, 0.25), 200) * 1e3
-        out["streaming_mw_v10_v11_native_B1024_M16_L128_D16"] = entry
+            entry[f"reference_{ver}_cuda_graph_us"] = graph_time_us(
+                torch, lambda: ref.streaming_mw(ver, q16, k16, v16, o16, 0.25, stream=s_cur()))
+        out["d16_native_B1024_M16_L128_gpu_time"] = entry
     q1, o1 = q16[:, 0].contiguous(), torch.zeros((1024, 16), device=dev)
     out["v7_5_native_B1024_S128_D16_single_query"] = {
         "reference_us": timeit(lambda: ref.v7_5_kernel(q1, k16, v16, o1), 200) * 1e3,
