@@ -465,11 +465,20 @@ int fa_forward_cross(const void* Q, const void* K, const void* V, float* O, int 
     int rc = current_device_state(&st);
     if (rc != FA_OK) return rc;
     const long long rows = static_cast<long long>(B) * H * Nq;
-    const long long ctas = (rows + 7) / 8;
-    if (ctas > 0x7fffffffll) return FA_ERR_BAD_SHAPE;
-    fa_fwd_d16_kernel<<<static_cast<unsigned>(ctas), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __half*>(Q), static_cast<const __half*>(K), static_cast<const __half*>(V), O, rows, Nq, Nkv,
-        scale * 1.4426950408889634f);
+    if (Nq >= 4) {  // four query rows per warp, K / V staged in shared memory
+      const int q_blocks = (Nq + 15) / 16;
+      const long long ctas = static_cast<long long>(B) * H * q_blocks;
+      if (ctas > 0x7fffffffll) return FA_ERR_BAD_SHAPE;
+      fa_fwd_d16_rows4_kernel<<<static_cast<unsigned>(ctas), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+          static_cast<const __half*>(Q), static_cast<const __half*>(K), static_cast<const __half*>(V), O, q_blocks, Nq, Nkv,
+          scale * 1.4426950408889634f);
+    } else {  // decode shapes (v7_5: one query per batch element): one warp per query row
+      const long long ctas = (rows + 7) / 8;
+      if (ctas > 0x7fffffffll) return FA_ERR_BAD_SHAPE;
+      fa_fwd_d16_kernel<<<static_cast<unsigned>(ctas), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+          static_cast<const __half*>(Q), static_cast<const __half*>(K), static_cast<const __half*>(V), O, rows, Nq, Nkv,
+          scale * 1.4426950408889634f);
+    }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? FA_OK : static_cast<int>(e);

@@ -84,4 +84,153 @@ __global__ void __launch_bounds__(256) fa_fwd_d16_kernel(const __half* __restric
         make_float4(acc[lane * 4], acc[lane * 4 + 1], acc[lane * 4 + 2], acc[lane * 4 + 3]);
 }
 
+// Same operator for Nq >= 4: a CTA of four warps takes 16 consecutive query rows of one (b,h), stages K / V in
+// shared memory 128 keys at a time (one 32 B row of each per thread) and every warp keeps FOUR query rows in
+// registers, so a key's K and V rows are converted once per four (row, key) pairs and the 64 partial outputs of a
+// lane are reduced across the warp by recursive halving (62 shuffles for four rows instead of 80 per row).
+__device__ __forceinline__ void unpack_half16(const uint4 a, const uint4 b, float* out) {
+  const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+    out[2 * i] = f.x;
+    out[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(128) fa_fwd_d16_rows4_kernel(const __half* __restrict__ Q, const __half* __restrict__ K,
+                                                               const __half* __restrict__ V, float* __restrict__ O,
+                                                               int q_blocks, int nq, int nkv, float scale_log2) {
+  __shared__ uint4 sK[128][2];  // 128 keys x 16 halfs
+  __shared__ uint4 sV[128][2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long bh = blockIdx.x / q_blocks;
+  const int row0 = (blockIdx.x % q_blocks) * 16 + warp * 4;  // first of this warp's four query rows
+  const __half* kb = K + bh * nkv * 16;
+  const __half* vb = V + bh * nkv * 16;
+  float q[4][16];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int row = min(row0 + r, nq - 1);  // rows past nq repeat the last row and are not stored
+    load_half16(Q + (bh * nq + row) * 16, q[r]);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) q[r][i] *= scale_log2;  // exp2 domain
+  }
+  float m_run[4], l_run[4], acc[4][16];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    m_run[r] = -CUDART_INF_F;
+    l_run[r] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[r][i] = 0.f;
+  }
+  for (int k0 = 0; k0 < nkv; k0 += 128) {
+    __syncthreads();  // the previous chunk has been consumed by every warp
+    {
+      const int key = k0 + threadIdx.x;
+      if (key < nkv) {
+        const uint4* kp = reinterpret_cast<const uint4*>(kb + static_cast<long long>(key) * 16);
+        const uint4* vp = reinterpret_cast<const uint4*>(vb + static_cast<long long>(key) * 16);
+        sK[threadIdx.x][0] = __ldg(kp);
+        sK[threadIdx.x][1] = __ldg(kp + 1);
+        sV[threadIdx.x][0] = __ldg(vp);
+        sV[threadIdx.x][1] = __ldg(vp + 1);
+      }
+    }
+    __syncthreads();
+    float s[4][4];  // [row][key slot]: this lane's keys are k0 + lane + 32 * slot
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int kl = lane + 32 * i;
+      if (k0 + kl < nkv) {
+        float kk[16];
+        unpack_half16(sK[kl][0], sK[kl][1], kk);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          float d = 0.f;
+#pragma unroll
+          for (int c = 0; c < 16; ++c) d = fmaf(q[r][c], kk[c], d);
+          s[r][i] = d;
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) s[r][i] = -CUDART_INF_F;
+      }
+    }
+    float pr[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      float mx = fmaxf(fmaxf(s[r][0], s[r][1]), fmaxf(s[r][2], s[r][3]));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      const float m_new = fmaxf(m_run[r], mx);  // finite: every chunk holds at least one valid key
+      const float alpha = ex2_fast(m_run[r] - m_new);  // first chunk: exp2(-inf) = 0
+      m_run[r] = m_new;
+      float ps = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        pr[r][i] = ex2_fast(s[r][i] - m_new);
+        ps += pr[r][i];
+      }
+      l_run[r] = l_run[r] * alpha + ps;  // lane-local partial sum; reduced across the warp at the end
+      if (alpha != 1.f) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) acc[r][c] *= alpha;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int kl = lane + 32 * i;
+      if (k0 + kl < nkv) {
+        float vv[16];
+        unpack_half16(sV[kl][0], sV[kl][1], vv);
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 16; ++c) acc[r][c] = fmaf(pr[r][i], vv[c], acc[r][c]);
+      }
+    }
+  }
+  // row sums across the warp, then the 64 partial outputs by recursive halving: after the step with lane offset
+  // `o` a lane keeps the half selected by that bit of its lane id, so it ends with two adjacent columns of one row
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], o);
+  }
+  float v64[64];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 16; ++c) v64[r * 16 + c] = acc[r][c];
+  int n = 32;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1, n >>= 1) {
+    const bool upper = (lane & o) != 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (j < n) {
+        const float send = upper ? v64[j] : v64[j + n];
+        const float keep = upper ? v64[j + n] : v64[j];
+        v64[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+      }
+    }
+  }
+  const int idx = ((lane >> 4) & 1) * 32 + ((lane >> 3) & 1) * 16 + ((lane >> 2) & 1) * 8 + ((lane >> 1) & 1) * 4 + (lane & 1) * 2;
+  const int r = idx >> 4, c = idx & 15;
+  if (row0 + r < nq) {
+    float lr = l_run[0];  // select without dynamic register indexing
+    lr = (r == 1) ? l_run[1] : lr;
+    lr = (r == 2) ? l_run[2] : lr;
+    lr = (r == 3) ? l_run[3] : lr;
+    const float inv = 1.f / lr;
+    *reinterpret_cast<float2*>(O + (bh * nq + row0 + r) * 16 + c) = make_float2(v64[0] * inv, v64[1] * inv);
+  }
+}
+
 }  // namespace fa
