@@ -10,7 +10,10 @@
  * or double accumulation exactly as the reference writes it) against the reference's own
  * functions compiled unmodified from /root/reference into oracle/_ref/ (see oracle/Makefile and
  * tests/test_oracle.py), and against the committed fixtures in tests/golden/ that those compiled
- * functions produced (tests/golden/make_golden.py).
+ * functions produced (tests/golden/make_golden.py).  One exception, marked where it is defined:
+ * fa_oracle_streaming_state_f16 restates a rule that exists in the reference as DEVICE code only (no
+ * host function to compile); it is pinned through its invariants and against the reference's
+ * streaming kernel run on the GPU.
  *
  * Build: gcc -O2 -ffp-contract=off -fopenmp -shared -fPIC (no -ffast-math: summation order and
  * rounding must match the reference's g++-compiled host code).
