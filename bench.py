@@ -176,6 +176,26 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(index):
+    """Pins this process to the CPUs NVML reports as local to GPU `index` (intersected with the CPUs the container
+    allows), so that the pinned host buffers of the end-to-end leg are first-touched on the GPU's NUMA node and
+    its H2D / D2H copies do not cross the socket interconnect.  Returns a short description for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        local = {i * 64 + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus = sorted(local & allowed)
+        if cpus and len(cpus) < len(allowed):
+            os.sched_setaffinity(0, cpus)
+            return f"bound to {len(cpus)} of {len(allowed)} CPUs local to GPU {index}"
+        return f"no narrower CPU set local to GPU {index} ({len(local & allowed)} of {len(allowed)} allowed CPUs are local)"
+    except Exception as e:  # noqa: BLE001
+        return f"not bound ({type(e).__name__})"
+
+
 def time_loop(torch, fn, steps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -199,6 +219,7 @@ def run_ours(args):
         raise RuntimeError("bench.py needs a B200: this framework has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)  # before any pinned host allocation: first touch decides the node
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -293,7 +314,8 @@ def run_ours(args):
                    "tokens_per_s": world * B * N / (ms_step * 1e-3)},
         "clocks": clocks.summary(),
         "e2e": {"value": e2e_value, "unit": "TFLOP/s", "h2d_bytes_per_step": 3 * tensor_bytes,
-                "d2h_bytes_per_step": tensor_bytes, "steps": e2e_steps, "api": "fa_forward_host (C ABI, pinned host buffers)"},
+                "d2h_bytes_per_step": tensor_bytes, "steps": e2e_steps, "api": "fa_forward_host (C ABI, pinned host buffers)",
+                "host_numa": numa},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "fa_fwd_kernel<128>", "achieved": achieved,
                      "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
