@@ -19,16 +19,23 @@
 
 namespace fa {
 
+// two packed halfs -> two floats without taking the address of a register (which would force local memory)
+__device__ __forceinline__ void half2_bits_to_floats(uint32_t w, float& lo, float& hi) {
+  lo = __half2float(__ushort_as_half(static_cast<unsigned short>(w & 0xffffu)));
+  hi = __half2float(__ushort_as_half(static_cast<unsigned short>(w >> 16)));
+}
+__device__ __forceinline__ void unpack_half16(const uint4 a, const uint4 b, float* out) {
+  half2_bits_to_floats(a.x, out[0], out[1]);
+  half2_bits_to_floats(a.y, out[2], out[3]);
+  half2_bits_to_floats(a.z, out[4], out[5]);
+  half2_bits_to_floats(a.w, out[6], out[7]);
+  half2_bits_to_floats(b.x, out[8], out[9]);
+  half2_bits_to_floats(b.y, out[10], out[11]);
+  half2_bits_to_floats(b.z, out[12], out[13]);
+  half2_bits_to_floats(b.w, out[14], out[15]);
+}
 __device__ __forceinline__ void load_half16(const __half* p, float* out) {
-  const uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
-  const uint4 b = __ldg(reinterpret_cast<const uint4*>(p) + 1);
-  const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
-    out[2 * i] = f.x;
-    out[2 * i + 1] = f.y;
-  }
+  unpack_half16(__ldg(reinterpret_cast<const uint4*>(p)), __ldg(reinterpret_cast<const uint4*>(p) + 1), out);
 }
 
 // Q [BH, Nq, 16], K, V [BH, Nkv, 16] fp16; O fp32 [BH, Nq, 16].  blockDim = 256 (8 rows per CTA).
@@ -79,24 +86,19 @@ __global__ void __launch_bounds__(256) fa_fwd_d16_kernel(const __half* __restric
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     acc[i] = v * inv;
   }
-  if (lane < 4)  // 16 floats = 64 B: four lanes store 16 B each
-    *reinterpret_cast<float4*>(O + row * 16 + lane * 4) =
-        make_float4(acc[lane * 4], acc[lane * 4 + 1], acc[lane * 4 + 2], acc[lane * 4 + 3]);
+  if (lane < 4) {  // 16 floats = 64 B: four lanes store 16 B each (selects, not a dynamically indexed register array)
+    float4 o4 = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    if (lane == 1) o4 = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    if (lane == 2) o4 = make_float4(acc[8], acc[9], acc[10], acc[11]);
+    if (lane == 3) o4 = make_float4(acc[12], acc[13], acc[14], acc[15]);
+    *reinterpret_cast<float4*>(O + row * 16 + lane * 4) = o4;
+  }
 }
 
 // Same operator for Nq >= 4: a CTA of four warps takes 16 consecutive query rows of one (b,h), stages K / V in
 // shared memory 128 keys at a time (one 32 B row of each per thread) and every warp keeps FOUR query rows in
 // registers, so a key's K and V rows are converted once per four (row, key) pairs and the 64 partial outputs of a
 // lane are reduced across the warp by recursive halving (62 shuffles for four rows instead of 80 per row).
-__device__ __forceinline__ void unpack_half16(const uint4 a, const uint4 b, float* out) {
-  const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
-    out[2 * i] = f.x;
-    out[2 * i + 1] = f.y;
-  }
-}
 __device__ __forceinline__ float ex2_fast(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
