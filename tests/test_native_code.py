@@ -61,3 +61,17 @@ def test_softmax_kernels_are_plain_bandwidth_kernels(sass):
     for body in _one(sass, "softmax_rows_reg_kernel"):
         assert "LDG.E.128" in body or "LDG.E.EF.128" in body or ".128" in body  # 128-bit global accesses
         assert "UTCHMMA" not in body and "HMMA" not in body
+
+
+def test_kernels_keep_their_state_in_registers():
+    """cuobjdump -res-usage: no kernel uses local memory arrays; the config-3 attention kernel, the GEMM, the softmax and
+    the D = 16 kernels have no stack frame at all (the D = 64 attention instantiation keeps one 8-byte spill slot)."""
+    import re
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-res-usage", fa.lib_path()], capture_output=True, text=True, check=True).stdout
+    entries = re.findall(r"Function (\S+):\s*\n\s*REG:(\d+) STACK:(\d+) SHARED:(\d+) LOCAL:(\d+)", out)
+    assert len(entries) >= 20
+    for name, reg, stack, shared, local in entries:
+        assert int(local) == 0, name
+        limit = 16 if "fa_fwd_kernelILi64" in name else 0
+        assert int(stack) <= limit, f"{name}: stack frame of {stack} bytes"
