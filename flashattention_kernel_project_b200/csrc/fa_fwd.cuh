@@ -92,6 +92,12 @@ constexpr float kLazyRescaleTau = 8.0f;  // log2 units: P stays below 2^8, far i
 // short bursts the MUFU-only build is as fast or faster (a warp's MUFU stall and its FMA work do not overlap), but a
 // launch then costs more energy, and the sustained rate is set by energy per launch.
 constexpr unsigned kPolyMask = FA_POLY_MASK;
+#ifndef FA_POLY_MASK_D64
+#define FA_POLY_MASK_D64 0x49
+#endif
+// D = 64 halves the tensor work per key, so the MUFU weighs more: same harness at 8 x 32 x 4096 x 64 -- 0x00 -> 676,
+// 0x11 -> 686, 0x49 (three pairs of eight, 37.5 %) -> 704, 0x55 -> 667 TFLOP/s.
+constexpr unsigned kPolyMaskD64 = FA_POLY_MASK_D64;
 
 // Schedule knobs (build-time; defaults are the measured best on B200, see DESIGN.md 3.1: period per 128 keys and tile
 // from the clock64 trace, config 3 -- head 0/8/12/16/20/24/32/48/64 keys x split 2..7 groups: 16 x 4 -> 3234 cycles,
@@ -290,6 +296,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
         // ---- exps, packed row sums, fp16 P written back over S; P is published to the MMA warp in two
         // chunks (keys [0,64) then [64,128)) so half of the PV MMAs overlap the tail of the softmax
         uint64_t lsum_a = pack_f32x2(0.f, 0.f), lsum_b = pack_f32x2(0.f, 0.f);
+        constexpr unsigned poly_mask = (D == 64) ? kPolyMaskD64 : kPolyMask;
         const float cy = c * (1.f / 128.f);                 // y = sat(s*cy + by) encodes x = 128*y - 120
         const float by = (neg_mc + 120.f) * (1.f / 128.f);
 #pragma unroll
@@ -303,13 +310,13 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
               p0 = pe[e]; p1 = pe[e + 1]; p2 = pe[e + 2]; p3 = pe[e + 3];
             } else {
               float x0, x1, x2, x3;
-              if ((kPolyMask >> (k / 2)) & 1u) {
+              if ((poly_mask >> (k / 2)) & 1u) {
                 exp2_poly_pair(pack_f32x2(ffma_sat(s[e + 0], cy, by), ffma_sat(s[e + 1], cy, by)), p0, p1);
               } else {
                 unpack_f32x2(ffma2(pack_f32x2(s[e + 0], s[e + 1]), c2, neg_mc2), x0, x1);
                 p0 = ex2_approx(x0); p1 = ex2_approx(x1);
               }
-              if ((kPolyMask >> (k / 2 + 1)) & 1u) {
+              if ((poly_mask >> (k / 2 + 1)) & 1u) {
                 exp2_poly_pair(pack_f32x2(ffma_sat(s[e + 2], cy, by), ffma_sat(s[e + 3], cy, by)), p2, p3);
               } else {
                 unpack_f32x2(ffma2(pack_f32x2(s[e + 2], s[e + 3]), c2, neg_mc2), x2, x3);

@@ -13,7 +13,7 @@ for p in sys.argv[1:]:
     L = ctypes.CDLL(os.path.join(ROOT, p), mode=ctypes.RTLD_LOCAL)
     L.fa_forward.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int] * 4 + [ctypes.c_float, ctypes.c_void_p]
     libs.append((os.path.basename(p), L))
-B, H, N, D = 8, 32, 4096, 128
+B, H, N, D = 8, 32, 4096, int(os.environ.get("FA_D", "128"))
 q, k, v = ((torch.rand((B, H, N, D), device="cuda") * 2 - 1).half() for _ in range(3))
 o = torch.empty_like(q)
 fl = 4.0 * B * H * N * N * D
