@@ -9,8 +9,10 @@ One JSON line on stdout (rank 0).  A "step" is one pass of the hot path (fa_forw
 of synthetic input.  value = whole-job TFLOP/s with inputs resident in HBM (FLOPs = 4*B*H*N^2*D, the
 reference's model, flashattn_forward_wmma_memprofile.cu:505-509); e2e = the same metric through the
 host-buffer C-ABI call (pinned host inputs, H2D + D2H inside the timed region).
-Multi-GPU: every rank runs the full per-GPU workload on its own (b,h) shards with no collective on
-the data path (weak scaling); time = max over ranks of the CUDA-event time.
+Multi-GPU (strong scaling): the B*H = 256 (b,h) units of config 3 are fixed and head-sharded -- rank r of N owns the
+contiguous slice shard_range(256, N, r) -- with no collective on the data path; value = whole-job FLOPs / the max over
+ranks of the CUDA-event time.  With N > 1 the line also carries extras.ring_cfg4: BASELINE config 4 (N = 65536) as the
+context-parallel ring through fa_ring_forward, with its parity against the CPU oracle, and the replica figure.
 """
 import argparse
 import json
@@ -206,6 +208,107 @@ def time_loop(torch, fn, steps):
     return e0.elapsed_time(e1)  # ms
 
 
+def link_probe(torch, dev, h2d_bytes, d2h_bytes, steps=3):
+    """The ceiling of the end-to-end leg on this box: plain pinned cudaMemcpyAsync of one step's bytes, host->device
+    and device->host at the same time on two streams (PCIe is full duplex), no kernel.  Every rank runs it at once,
+    so at N GPUs it also shows what the host can feed N links with.  Returns ms per step."""
+    src = torch.empty(h2d_bytes, dtype=torch.uint8).pin_memory()
+    dst = torch.empty(h2d_bytes, dtype=torch.uint8, device=dev)
+    back_src = torch.empty(d2h_bytes, dtype=torch.uint8, device=dev)
+    back_dst = torch.empty(d2h_bytes, dtype=torch.uint8).pin_memory()
+    s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+    def once():
+        with torch.cuda.stream(s_in):
+            dst.copy_(src, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            back_dst.copy_(back_src, non_blocking=True)
+        s_in.synchronize()
+        s_out.synchronize()
+    once()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        once()
+    return (time.perf_counter() - t0) * 1e3 / steps
+
+
+def ring_cfg4(torch, dist, fa, dev, rank, world):
+    """BASELINE config 4 (B=1, H=32, N=65536, D=128) as the context-parallel ring over the ranks of this job, through
+    the C ABI fa_ring_forward; device time = max over ranks; checked on sampled rows against the CPU oracle."""
+    import numpy as np
+    B, H, N, D = 1, 32, 65536, 128
+    n = N // world
+    scale = D ** -0.5
+    g = torch.Generator(device=dev).manual_seed(7 + rank)
+    q, k, v = ((torch.rand((B, H, n, D), device=dev, generator=g) * 2 - 1).half() for _ in range(3))
+    out = torch.empty_like(q)
+    ws = fa.RingWorkspace(q.shape, world, dev)
+    run = lambda: fa.ring_forward(q, k, v, scale, out=out, workspace=ws)
+
+    def timed(fn, iters):
+        dist.barrier()
+        torch.cuda.synchronize()
+        ms = time_loop(torch, fn, iters) / iters
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    for _ in range(2):
+        run()
+    ms = timed(run, 5)
+    # compute-only lower bound: the same `world` partial steps with no exchange
+    o_acc = torch.empty((B, H, n, D), dtype=torch.float32, device=dev)
+    m = torch.empty((B, H, n), dtype=torch.float32, device=dev)
+    l = torch.empty((B, H, n), dtype=torch.float32, device=dev)
+    of = torch.empty_like(q)
+
+    def compute_only():
+        for s in range(world):
+            fa.fa_forward_partial(q, k, v, o_acc, m, l, scale, s == 0, s == world - 1, of)
+    compute_only()
+    ms_c = timed(compute_only, 5)
+    # parity: 64 query rows of head 5 on rank 0 and 64 on the last rank, against the oracle on the gathered K/V
+    head = 5
+    kv = [torch.empty((2, n, D), dtype=torch.float16, device=dev) for _ in range(world)]
+    dist.all_gather(kv, torch.stack((k[0, head], v[0, head])))
+    rows = np.unique(np.concatenate([[0, 1, 127, 128, 255, 256, n - 1], np.random.default_rng(0).integers(0, n, 64)]))[:64]
+    mine = torch.stack((q[0, head][rows], out[0, head][rows]))
+    qs = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(qs, mine)
+    # one GPU alone on the whole problem: the reference point of the speed-up
+    ms_1 = None
+    if rank == 0:
+        del o_acc, of
+        qf, kf, vf = ((torch.rand((B, H, N, D), device=dev) * 2 - 1).half() for _ in range(3))
+        o1 = torch.empty_like(qf)
+        one = lambda: fa.fa_forward(qf, kf, vf, scale, out=o1)
+        one()
+        torch.cuda.synchronize()
+        ms_1 = time_loop(torch, one, 2) / 2
+        del qf, kf, vf, o1
+    dist.barrier()
+    if rank != 0:
+        return None
+    from tests.oracle_lib import Oracle
+    orc = Oracle()
+    k_all = torch.cat([x[0] for x in kv]).cpu().numpy()[None]
+    v_all = torch.cat([x[1] for x in kv]).cpu().numpy()[None]
+    rel, mx = 0.0, 0.0
+    for r in (0, world - 1):
+        qr, got = qs[r][0].cpu().numpy()[None], qs[r][1].float().cpu().numpy()
+        ref = orc.attention_f16_rows(qr, k_all, v_all, scale, np.arange(qr.shape[1]))
+        rel, mx = max(rel, orc.rel_l2(got, ref)), max(mx, orc.max_abs(got, ref))
+    fl = flops(B, H, N, D)
+    return {"config": "fp16 attention fwd B=1,H=32,N=65536,D=128, sequence split over the ranks (ring / context parallel)",
+            "api": "fa_ring_forward (C ABI): all partial-attention launches + grouped ncclSend/ncclRecv enqueued from C++",
+            "n_gpus": world, "ms": ms, "tflops_total": fl / ms / 1e9, "ms_compute_only": ms_c,
+            "exchange_overhead": ms / ms_c - 1.0, "ms_1gpu": ms_1, "speedup_vs_1gpu": ms_1 / ms,
+            "exchange_bytes_per_gpu": 2 * (world - 1) * B * H * n * D * 2,
+            "parity": {"rows": int(2 * len(rows)), "ranks": [0, world - 1], "head": head, "rel_l2": rel, "max_abs": mx,
+                       "tolerance": {"rel_l2": 1e-3, "max_abs": 2e-3}, "ok": bool(rel <= 1e-3 and mx <= 2e-3),
+                       "oracle": "cpu_reference restatement (oracle/fa_oracle.c) on the K/V gathered from all ranks"}}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -223,11 +326,15 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    # BASELINE config 3, head-sharded: the B*H = 256 (b,h) units are FIXED; rank r owns the contiguous slice
+    # shard_range(256, world, r) (GPU g takes bh in [g*256/G, (g+1)*256/G)), no collective on the data path.
     B, H, N, D = (WORKLOAD[x] for x in "BHND")
     scale = 1.0 / D ** 0.5
+    bh0, bh1 = fa.shard_range(B * H, world, rank)
+    nbh = bh1 - bh0
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    mk = lambda: (torch.rand((B, H, N, D), device=dev, generator=g) * 2 - 1).half()  # the reference's uniform(-1,1)
-    q, k, v = mk(), mk(), mk()
+    mk = lambda n: (torch.rand((1, n, N, D), device=dev, generator=g) * 2 - 1).half()  # the reference's uniform(-1,1)
+    q, k, v = mk(nbh), mk(nbh), mk(nbh)
     o = torch.empty_like(q)
     step = lambda: fa.fa_forward(q, k, v, scale, out=o)
 
@@ -236,7 +343,13 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # Burst figure first, while the part is still cool: 3 + 20 launches (~45 ms) finish before the power cap pulls the
+    def max_over_ranks(x):
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # Burst figure first, while the part is still cool: 3 + 20 launches finish before the power cap pulls the
     # clock down.  Reported next to the sustained number below, against the burst cuBLAS peak.
     for _ in range(3):
         step()
@@ -257,13 +370,10 @@ def run_ours(args):
             while time.time() < t_end:
                 step()
             torch.cuda.synchronize()
-    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    ms_step = ms_max / args.steps
-    per_gpu_flops = flops(B, H, N, D)
-    value = world * per_gpu_flops / (ms_step * 1e-3) / 1e12
+    ms_step = max_over_ranks(ms_total) / args.steps
+    total_flops = flops(B, H, N, D)               # the whole job, whatever the number of ranks
+    rank_flops = flops(1, nbh, N, D)              # this rank's slice
+    value = total_flops / (ms_step * 1e-3) / 1e12
 
     # ---- end to end through the host-buffer C-ABI call (pinned host memory, copies timed) ----
     e2e_steps = max(2, min(args.steps, 8))
@@ -275,13 +385,33 @@ def run_ours(args):
     t0 = time.perf_counter()
     ev_ms = time_loop(torch, host_step, e2e_steps)
     wall_ms = (time.perf_counter() - t0) * 1e3
-    e2e_ms = max(ev_ms, wall_ms) / e2e_steps
-    t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * per_gpu_flops / (float(t.item()) * 1e-3) / 1e12
-    tensor_bytes = q.numel() * 2
+    e2e_ms = max_over_ranks(max(ev_ms, wall_ms) / e2e_steps)
+    e2e_value = total_flops / (e2e_ms * 1e-3) / 1e12
+    tensor_bytes = q.numel() * 2  # this rank's share of one tensor
     fa.load_library().fa_host_release()
+    del hq, hk, hv, ho
+    barrier()
+    link_ms = max_over_ranks(link_probe(torch, dev, 3 * tensor_bytes, tensor_bytes))
+
+    multi = {}
+    if world > 1 and not args.no_extras:
+        # the replica (weak-scaling) figure of round 1, for reference: every rank the full B*H = 256
+        del q, k, v, o
+        qr, kr, vr = mk(B * H), mk(B * H), mk(B * H)
+        orr = torch.empty_like(qr)
+        rstep = lambda: fa.fa_forward(qr, kr, vr, scale, out=orr)
+        for _ in range(3):
+            rstep()
+        barrier()
+        rms = max_over_ranks(time_loop(torch, rstep, 20) / 20)
+        multi["replica_weak_scaling"] = {"value": world * total_flops / (rms * 1e-3) / 1e12, "unit": "TFLOP/s",
+                                         "ms_per_step": rms, "note": "every rank runs all 256 (b,h): round 1's bench"}
+        del qr, kr, vr, orr
+        torch.cuda.empty_cache()
+        try:
+            multi["ring_cfg4"] = ring_cfg4(torch, dist, fa, dev, rank, world)
+        except Exception as e:  # noqa: BLE001
+            multi["ring_cfg4"] = {"error": f"{type(e).__name__}: {e}"[:300]}
 
     if rank != 0:
         if world > 1:
@@ -290,32 +420,38 @@ def run_ours(args):
 
     peaks, peak_src = load_peaks()
     kernel_ms = ms_total / args.steps  # rank 0's own average launch duration (back-to-back launches, one kernel per step)
-    achieved = per_gpu_flops / (kernel_ms * 1e-3) / 1e12
-    burst = per_gpu_flops / (burst_ms * 1e-3) / 1e12
+    achieved = rank_flops / (kernel_ms * 1e-3) / 1e12
+    burst = rank_flops / (burst_ms * 1e-3) / 1e12
     # The denominator follows how the kernel was timed: inside a long back-to-back run the part sits at its power cap,
     # so the comparable cuBLAS figure is the sustained one; a short timed region compares with the burst figure.
     long_run = ms_total >= 250.0 and "bf16_tflops_sustained" in peaks
     peak = peaks["bf16_tflops_sustained"] if long_run else peaks["bf16_tflops"]
     peak_kind = ("sustained cuBLAS bf16 (kernel timed inside a %.0f ms back-to-back run)" % ms_total) if long_run \
         else "burst cuBLAS bf16 (timed region %.0f ms)" % ms_total
-    traffic = None
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "fa_fwd_traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and world == 1:
         with open(tpath) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+            tj = json.load(f)
+        traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
+    shard_note = "all 256 (b,h) on one GPU" if world == 1 else \
+        f"head-sharded over {world} GPUs: rank r owns (b,h) in shard_range(256, {world}, r), {nbh} per GPU, no collective"
     line = {
         "metric": "attention fwd TFLOP/s", "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-        "config": {"workload": "fp16 non-causal attention fwd B=8,H=32,N=4096,D=128 per GPU (BASELINE config 3); "
-                               "ranks hold independent (b,h) shards, no collective",
-                   **WORKLOAD, "scale": scale, "inputs": "uniform(-1,1) fp16, resident in HBM",
-                   "l2": "Q+K+V+O = 1.07 GB per step, larger than the 126 MB L2 (no flush needed)",
-                   "tokens_per_s": world * B * N / (ms_step * 1e-3)},
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+        "config": {"workload": "fp16 non-causal attention fwd B=8,H=32,N=4096,D=128 (BASELINE config 3), " + shard_note,
+                   **WORKLOAD, "bh_per_gpu": nbh, "scale": scale, "inputs": "uniform(-1,1) fp16, resident in HBM",
+                   "l2": "Q+K+V+O = %.2f GB per GPU and step%s" % (4 * tensor_bytes / 1e9,
+                         ", larger than the 126 MB L2 (no flush needed)" if 4 * tensor_bytes > 126e6 else ""),
+                   "tokens_per_s": B * N / (ms_step * 1e-3)},
         "clocks": clocks.summary(),
         "e2e": {"value": e2e_value, "unit": "TFLOP/s", "h2d_bytes_per_step": 3 * tensor_bytes,
-                "d2h_bytes_per_step": tensor_bytes, "steps": e2e_steps, "api": "fa_forward_host (C ABI, pinned host buffers)",
-                "host_numa": numa},
+                "d2h_bytes_per_step": tensor_bytes, "bytes_are": "per GPU", "steps": e2e_steps,
+                "ms_per_step": e2e_ms, "api": "fa_forward_host (C ABI, pinned host buffers)", "host_numa": numa,
+                "link_ms_per_step": link_ms, "link_frac": link_ms / e2e_ms,
+                "link_probe": "the same bytes as plain pinned cudaMemcpyAsync, H2D and D2H concurrently, all ranks at once, "
+                              "no kernel: link_frac = probe time / e2e time (1.0 = the call costs no more than its copies)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "fa_fwd_kernel<128>", "achieved": achieved,
                      "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
@@ -324,12 +460,16 @@ def run_ours(args):
                      "frac_of_burst_peak": achieved / peaks["bf16_tflops"],
                      "frac_of_sustained_peak": achieved / peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]),
                      "frac_of_nominal_2250": achieved / NOMINAL_TFLOPS,
-                     "algorithmic_flops_per_launch": per_gpu_flops, "traffic": traffic},
+                     "algorithmic_flops_per_launch": rank_flops, "traffic": traffic, "traffic_source": traffic_src},
     }
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_attention_rate(args.cpu_seconds)
     if world == 1 and not args.no_extras:
+        del q, k, v, o
+        torch.cuda.empty_cache()
         line["extras"] = extras(torch, fa, dev, peaks)
+    elif multi:
+        line["extras"] = multi
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

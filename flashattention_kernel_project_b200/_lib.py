@@ -14,11 +14,14 @@ c_float_p = ctypes.c_void_p  # device / host addresses are passed as integers
 # name -> (restype, argtypes); kept in sync with include/fa_b200.h (tests/test_abi.py checks it)
 SIGNATURES = {
     "fa_version": (c_int, []),
+    "fa_init": (c_int, []),
     "fa_strerror": (ctypes.c_char_p, [c_int]),
     "fa_forward": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_float, c_void_p]),
     "fa_forward_f32out": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_float, c_void_p]),
     "fa_forward_cross": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_float, c_void_p]),
     "fa_forward_partial": (c_int, [c_void_p] * 6 + [c_int] * 5 + [c_float, c_int, c_int, c_void_p, c_void_p]),
+    "fa_ring_workspace_bytes": (ctypes.c_size_t, [c_int] * 6),
+    "fa_ring_forward": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_float, c_int, c_int, c_void_p, c_void_p, ctypes.c_size_t, c_void_p]),
     "gemm_fused_epilogue": (c_int, [c_void_p] * 5 + [c_int] * 3 + [c_void_p]),
     "gemm_batched": (c_int, [c_void_p] * 3 + [c_int] * 5 + [c_float, c_void_p]),
     "softmax_rows": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
@@ -30,6 +33,8 @@ SIGNATURES = {
     "fa_host_release": (c_int, []),
     "fa_last_debug": (c_int, [ctypes.POINTER(ctypes.c_uint), c_int]),
     "fa_launch_count": (ctypes.c_ulonglong, []),
+    "fa_plan_segments": (c_int, [c_int] * 5 + [ctypes.POINTER(c_int), c_int]),
+    "fa_map_cache_stats": (c_int, [ctypes.POINTER(ctypes.c_ulonglong)] * 2),
 }
 
 

@@ -6,6 +6,8 @@
 // <<<>>> on the default stream -> D2H, e.g. flashattn_warp_spc/flashattn_streaming_16x32_2warp_softmax_v12i.cu:298-393)
 // that aborts through CHECK_CUDA (:21-29).  Here the same flow is behind *_host entry points and
 // every failure is a return code.
+#include <dlfcn.h>
+
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -23,6 +25,7 @@ namespace {
 using namespace fa;
 
 constexpr int kMaxDevices = 64;
+constexpr int kMaxRingWorld = 64;
 std::atomic<unsigned long long> g_launches{0};
 
 // ---- driver entry point: cuTensorMapEncodeTiled without linking libcuda -----------------
@@ -42,9 +45,64 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// Bounded, mutex-protected cache of encoded tensor maps.  A map is a pure function of
+// (base, element type, extents, box), so an entry never goes stale; a small-shape call (BASELINE config 1 is 4 us of
+// GPU time) otherwise spends more host time in four cuTensorMapEncodeTiled calls than the GPU spends computing.
+struct MapKey {
+  const void* base;
+  uint64_t dims[3];
+  uint32_t box[3];
+  int dt, rank;
+  bool operator==(const MapKey& o) const {
+    return base == o.base && dt == o.dt && rank == o.rank && dims[0] == o.dims[0] && dims[1] == o.dims[1] &&
+           dims[2] == o.dims[2] && box[0] == o.box[0] && box[1] == o.box[1] && box[2] == o.box[2];
+  }
+};
+constexpr int kMapCacheEntries = 64;
+struct MapCache {
+  std::mutex mu;
+  MapKey keys[kMapCacheEntries];
+  CUtensorMap maps[kMapCacheEntries];
+  int used = 0, next = 0;
+};
+MapCache g_map_cache;
+std::atomic<unsigned long long> g_map_hits{0}, g_map_misses{0};
+
+int encode_map(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, const void* base, int rank,
+               const uint64_t* dims, const uint32_t* box);
+
 // rank-2/3 tiled map over a row-major tensor whose innermost extent is dims[0]; 128B swizzle.
 int make_map(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, const void* base, int rank,
              const uint64_t* dims, const uint32_t* box) {
+  MapKey key{};
+  key.base = base;
+  key.dt = static_cast<int>(dt);
+  key.rank = rank;
+  for (int i = 0; i < rank; ++i) {
+    key.dims[i] = dims[i];
+    key.box[i] = box[i];
+  }
+  {
+    std::lock_guard<std::mutex> lock(g_map_cache.mu);
+    for (int i = 0; i < g_map_cache.used; ++i)
+      if (g_map_cache.keys[i] == key) {
+        *map = g_map_cache.maps[i];
+        g_map_hits.fetch_add(1, std::memory_order_relaxed);
+        return FA_OK;
+      }
+  }
+  const int rc = encode_map(map, dt, elem_bytes, base, rank, dims, box);
+  if (rc != FA_OK) return rc;
+  g_map_misses.fetch_add(1, std::memory_order_relaxed);
+  std::lock_guard<std::mutex> lock(g_map_cache.mu);
+  const int slot = g_map_cache.used < kMapCacheEntries ? g_map_cache.used++ : (g_map_cache.next++ % kMapCacheEntries);
+  g_map_cache.keys[slot] = key;
+  g_map_cache.maps[slot] = *map;
+  return FA_OK;
+}
+
+int encode_map(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, const void* base, int rank,
+               const uint64_t* dims, const uint32_t* box) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) return FA_ERR_DRIVER_ENTRY;
   cuuint64_t gdim[3];
@@ -70,6 +128,14 @@ struct DeviceState {
   bool is_sm100 = false;
   int sm_count = 0;
   bool attr_fa64 = false, attr_fa128 = false, attr_gemm = false, attr_gemm_t = false;
+  // stream-ordered pool for the attention kernel's tail workspace (allocated and freed on the caller's stream
+  // around the launch, so concurrent launches on different streams and captured graphs each own theirs)
+  bool pool_tried = false;
+  cudaMemPool_t pool = nullptr;
+  // ring attention: a high-priority side stream for the K/V exchange and the events that tie it to the caller's stream
+  bool ring_ready = false;
+  cudaStream_t s_ring = nullptr;
+  cudaEvent_t ev_ring_ready = nullptr, ev_ring_recv[kMaxRingWorld], ev_ring_step[kMaxRingWorld];
   // scratch for the *_host entry points
   void* scratch[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   size_t scratch_bytes[6] = {0, 0, 0, 0, 0, 0};
@@ -103,6 +169,20 @@ int current_device_state(DeviceState** out) {
     cudaDeviceGetAttribute(&st.sm_count, cudaDevAttrMultiProcessorCount, dev);
     st.is_sm100 = (major == 10);
     st.probed = true;
+  }
+  if (st.is_sm100 && !st.pool_tried) {
+    st.pool_tried = true;
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    if (cudaMemPoolCreate(&st.pool, &props) == cudaSuccess) {
+      unsigned long long keep = ~0ull;  // never hand the (<= 40 MB) workspace back to the driver between launches
+      cudaMemPoolSetAttribute(st.pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    } else {
+      (void)cudaGetLastError();
+      st.pool = nullptr;  // no pool: the tail of the grid is not cut (fa_plan)
+    }
   }
   if (!st.is_sm100) return FA_ERR_NO_DEVICE;
   if (g_dbg_host == nullptr) {
@@ -158,6 +238,43 @@ struct FaCall {
   int mode, is_first, is_last;
 };
 
+// How the grid is cut (fa_fwd.cuh, FaSegment).  Items beyond the last full wave of `sms` CTAs are cut along K/V into
+// equal spans, one per SM, when that shortens the last wave: whole items cost nkv_tiles iterations each, a span costs
+// its length plus about two iterations of prologue and merge.
+struct FaPlan {
+  int items_full, tail_items, tail_ctas;
+};
+bool tail_split_enabled() {
+  static const bool on = [] {
+    const char* e = std::getenv("FA_TAIL_SPLIT");
+    return e == nullptr || std::atoi(e) != 0;
+  }();
+  return on;
+}
+int tail_split_cost() {  // key-tile iterations charged to a cut span for its prologue and merge (FA_TAIL_COST, default 2)
+  static const int cost = [] {
+    const char* e = std::getenv("FA_TAIL_COST");
+    return e != nullptr ? std::atoi(e) : 2;
+  }();
+  return cost;
+}
+FaPlan fa_plan(long long items, int nkv_tiles, int sms, bool have_pool) {
+  FaPlan plan{static_cast<int>(items), 0, 0};
+  if (!have_pool || !tail_split_enabled() || sms <= 0) return plan;
+  const long long rest = items % sms;
+  if (rest == 0) return plan;
+  const long long total = rest * nkv_tiles;         // key-tile iterations of the partial wave
+  long long n = total / 2 < sms ? total / 2 : sms;  // spans of at least two key tiles
+  if (n <= rest) return plan;
+  const long long span = (total + n - 1) / n;
+  if (span + tail_split_cost() >= nkv_tiles) return plan;
+  if ((total + 1) * n >= 0x7fffffffll) return plan;  // the kernel's span arithmetic is 32-bit
+  plan.items_full = static_cast<int>(items - rest);
+  plan.tail_items = static_cast<int>(rest);
+  plan.tail_ctas = static_cast<int>(n);
+  return plan;
+}
+
 template <int D>
 int launch_fa(DeviceState* st, const FaCall& c, cudaStream_t stream) {
   using Cfg = FaCfg<D>;
@@ -198,11 +315,37 @@ int launch_fa(DeviceState* st, const FaCall& c, cudaStream_t stream) {
   p.trace = g_trace_buf;
   p.trace_cta = g_trace_cta;
 #endif
-  const uint64_t grid = BH * static_cast<uint64_t>(p.q_blocks);
-  if (grid == 0 || grid > 0x7fffffffull) return FA_ERR_BAD_SHAPE;
-  fa_fwd_kernel<D><<<static_cast<unsigned>(grid), Cfg::kThreads, Cfg::kSmemBytes, stream>>>(mq, mk, mv, mo, p);
+  const uint64_t items = BH * static_cast<uint64_t>(p.q_blocks);
+  if (items == 0 || items > 0x7fffffffull) return FA_ERR_BAD_SHAPE;
+  const FaPlan plan = fa_plan(static_cast<long long>(items), (c.Nkv + Cfg::kKT - 1) / Cfg::kKT, st->sm_count,
+                              st->pool != nullptr);
+  p.items_full = plan.items_full;
+  p.tail_items = plan.tail_items;
+  p.tail_ctas = plan.tail_ctas;
+  p.ws = nullptr;
+  p.ws_count = nullptr;
+  void* ws = nullptr;
+  if (plan.tail_ctas > 0) {
+    // [counters, padded to 256 B][tail_ctas * 2 slots of (D + 2) * 256 floats]
+    const size_t count_bytes = (static_cast<size_t>(plan.tail_items) * 4 + 255) & ~static_cast<size_t>(255);
+    const size_t bytes = count_bytes + static_cast<size_t>(plan.tail_ctas) * 2 * (D + 2) * 256 * 4;
+    cudaError_t e = cudaMallocFromPoolAsync(&ws, bytes, st->pool, stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ws, 0, count_bytes, stream);
+    if (e != cudaSuccess) {
+      if (ws != nullptr) cudaFreeAsync(ws, stream);
+      return static_cast<int>(e);
+    }
+    p.ws_count = static_cast<unsigned int*>(ws);
+    p.ws = reinterpret_cast<float*>(static_cast<char*>(ws) + count_bytes);
+  }
+  const unsigned grid = static_cast<unsigned>(plan.items_full + plan.tail_ctas);
+  fa_fwd_kernel<D><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(mq, mk, mv, mo, p);
   g_launches.fetch_add(1, std::memory_order_relaxed);
-  const cudaError_t e = cudaGetLastError();
+  cudaError_t e = cudaGetLastError();
+  if (ws != nullptr) {
+    const cudaError_t ef = cudaFreeAsync(ws, stream);
+    if (e == cudaSuccess) e = ef;
+  }
   return e == cudaSuccess ? FA_OK : static_cast<int>(e);
 }
 
@@ -372,6 +515,17 @@ int scratch_get(DeviceState* st, int slot, size_t bytes, void** out) {
     if (e__ != cudaSuccess) return static_cast<int>(e__); \
   } while (0)
 
+// Inside the chunk loops of the *_host entry points: a failing call must not leave earlier chunks' copies running
+// against the caller's buffers (and the scratch, which the next call reuses) -- drain the pipeline, then return.
+#define FA_PIPE_TRY(st, expr)                           \
+  do {                                                  \
+    cudaError_t e__ = (expr);                           \
+    if (e__ != cudaSuccess) {                           \
+      host_pipe_drain(st);                              \
+      return static_cast<int>(e__);                     \
+    }                                                   \
+  } while (0)
+
 // Streams and events of the host-buffer pipeline, created once per device.
 int host_pipe_init(DeviceState* st) {
   std::lock_guard<std::mutex> lock(g_mutex);
@@ -412,12 +566,90 @@ int host_chunks(size_t total_bytes, long long units) {
   return n < 1 ? 1 : static_cast<int>(n);
 }
 
+
+// ---- ring / context-parallel attention: NCCL resolved at run time ---------------------------------------------
+// The library does not link NCCL: a process that never calls fa_ring_forward (every C program above) needs none.
+// The symbols come from the libnccl.so.2 already loaded into the process (the one that created the caller's
+// communicator -- torch's bundled copy under torchrun), else from the system's.
+struct NcclApi {
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  bool ok = false;
+};
+const NcclApi& nccl_api() {
+  static NcclApi api = [] {
+    NcclApi a;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (h == nullptr) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (h == nullptr) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (h == nullptr) return a;
+    a.GroupStart = reinterpret_cast<int (*)()>(dlsym(h, "ncclGroupStart"));
+    a.GroupEnd = reinterpret_cast<int (*)()>(dlsym(h, "ncclGroupEnd"));
+    a.Send = reinterpret_cast<int (*)(const void*, size_t, int, int, void*, cudaStream_t)>(dlsym(h, "ncclSend"));
+    a.Recv = reinterpret_cast<int (*)(void*, size_t, int, int, void*, cudaStream_t)>(dlsym(h, "ncclRecv"));
+    a.ok = a.GroupStart != nullptr && a.GroupEnd != nullptr && a.Send != nullptr && a.Recv != nullptr;
+    return a;
+  }();
+  return api;
+}
+constexpr int kNcclUint8 = 1;  // ncclDataType_t: ncclInt8 = 0, ncclUint8 = 1 (nccl.h); shards travel as bytes
+
+int ring_init(DeviceState* st) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  if (st->ring_ready) return FA_OK;
+  int lo = 0, hi = 0;
+  FA_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  // The attention kernel holds every SM with one 227 KB CTA; NCCL's send/recv kernel only gets SMs while it runs if
+  // its stream outranks the compute stream (measured: 1.5 ms vs 14-19 ms for a 512 MiB exchange next to a 15 ms launch).
+  FA_CUDA_TRY(cudaStreamCreateWithPriority(&st->s_ring, cudaStreamNonBlocking, hi));
+  FA_CUDA_TRY(cudaEventCreateWithFlags(&st->ev_ring_ready, cudaEventDisableTiming));
+  for (int i = 0; i < kMaxRingWorld; ++i) {
+    FA_CUDA_TRY(cudaEventCreateWithFlags(&st->ev_ring_recv[i], cudaEventDisableTiming));
+    FA_CUDA_TRY(cudaEventCreateWithFlags(&st->ev_ring_step[i], cudaEventDisableTiming));
+  }
+  st->ring_ready = true;
+  return FA_OK;
+}
+
+struct RingLayout {
+  size_t state_o, state_m, state_l, kv, shard_bytes, total;
+  int depth;
+};
+// [O_acc fp32 | m | l | depth x (K shard, V shard)], every part 256-byte aligned
+RingLayout ring_layout(int B, int H, int n, int D, int world, size_t workspace_bytes) {
+  auto up = [](size_t x) { return (x + 255) & ~static_cast<size_t>(255); };
+  RingLayout L{};
+  const size_t rows = static_cast<size_t>(B) * H * n;
+  L.shard_bytes = up(rows * D * 2);
+  L.state_o = 0;
+  L.state_m = up(rows * D * 4);
+  L.state_l = L.state_m + up(rows * 4);
+  L.kv = L.state_l + up(rows * 4);
+  const int want = world - 1;
+  int depth = want;
+  if (workspace_bytes != 0) {
+    const size_t room = workspace_bytes > L.kv ? workspace_bytes - L.kv : 0;
+    const size_t fit = room / (2 * L.shard_bytes);
+    depth = fit < static_cast<size_t>(want) ? static_cast<int>(fit) : want;
+  }
+  L.depth = depth;
+  L.total = L.kv + static_cast<size_t>(depth) * 2 * L.shard_bytes;
+  return L;
+}
+
 }  // namespace
 
 // =========================================== C ABI ==========================================
 extern "C" {
 
-int fa_version(void) { return 100; }
+int fa_version(void) { return 200; }
+
+int fa_init(void) {
+  DeviceState* st = nullptr;
+  return current_device_state(&st);
+}
 
 const char* fa_strerror(int code) {
   switch (code) {
@@ -429,6 +661,7 @@ const char* fa_strerror(int code) {
     case FA_ERR_NO_DEVICE: return "current device is not an sm_100 (B200) GPU; there is no CPU fallback";
     case FA_ERR_DRIVER_ENTRY: return "cuTensorMapEncodeTiled unavailable or failed";
     case FA_ERR_BAD_ARGUMENT: return "bad argument";
+    case FA_ERR_NCCL: return "NCCL call failed";
     default: break;
   }
   if (code > 0) return cudaGetErrorString(static_cast<cudaError_t>(code));
@@ -452,6 +685,79 @@ int fa_forward_partial(const void* Q, const void* K, const void* V, float* O_acc
   FaCall c{Q, K, V, is_last ? O_final : nullptr, O_acc, m, l, B, H, Nq, Nkv, D, scale, FA_MODE_STATE,
            is_first ? 1 : 0, is_last ? 1 : 0};
   return run_fa(c, stream);
+}
+
+size_t fa_ring_workspace_bytes(int B, int H, int n, int D, int world, int depth) {
+  if (B <= 0 || H <= 0 || n <= 0 || D <= 0 || world <= 0) return 0;
+  RingLayout L = ring_layout(B, H, n, D, world, 0);
+  if (depth > 0 && depth < L.depth) L.total = L.kv + static_cast<size_t>(depth) * 2 * L.shard_bytes;
+  return L.total;
+}
+
+int fa_ring_forward(const void* Q, const void* K, const void* V, void* O, int B, int H, int n, int D, float scale,
+                    int rank, int world, void* nccl_comm, void* workspace, size_t workspace_bytes, void* stream) {
+  if (B <= 0 || H <= 0 || n <= 0) return FA_ERR_BAD_SHAPE;
+  if (D != 64 && D != 128) return FA_ERR_BAD_HEAD_DIM;
+  if (world <= 0 || world > kMaxRingWorld || rank < 0 || rank >= world) return FA_ERR_BAD_ARGUMENT;
+  if (Q == nullptr || K == nullptr || V == nullptr || O == nullptr || workspace == nullptr) return FA_ERR_NULL_POINTER;
+  if (world > 1 && nccl_comm == nullptr) return FA_ERR_NULL_POINTER;
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255u) != 0) return FA_ERR_MISALIGNED;
+  const RingLayout L = ring_layout(B, H, n, D, world, workspace_bytes);
+  if (workspace_bytes < L.kv || (world > 1 && L.depth < 1)) return FA_ERR_BAD_ARGUMENT;
+  DeviceState* st = nullptr;
+  int rc = current_device_state(&st);
+  if (rc != FA_OK) return rc;
+  char* const ws = static_cast<char*>(workspace);
+  float* const o_acc = reinterpret_cast<float*>(ws + L.state_o);
+  float* const m = reinterpret_cast<float*>(ws + L.state_m);
+  float* const l = reinterpret_cast<float*>(ws + L.state_l);
+  const cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (world == 1) return fa_forward_partial(Q, K, V, o_acc, m, l, B, H, n, n, D, scale, 1, 1, O, stream);
+
+  const NcclApi& nccl = nccl_api();
+  if (!nccl.ok) return FA_ERR_DRIVER_ENTRY;
+  if ((rc = ring_init(st)) != FA_OK) return rc;
+  std::lock_guard<std::mutex> ring_lock(st->host_mu);  // one enqueue at a time per device: the events are shared
+  const size_t bytes = static_cast<size_t>(B) * H * n * D * 2;
+  const int depth = L.depth;
+  auto kbuf = [&](int slot) { return ws + L.kv + static_cast<size_t>(slot) * 2 * L.shard_bytes; };
+  // Exchange x (1 <= x < world): this rank's OWN shard goes to rank + x and the shard of rank - x arrives.  K/V are
+  // read-only, so nothing is passed along: the world - 1 exchanges do not depend on each other and are enqueued as
+  // far ahead as the workspace has buffers (all of them with the default size), each one grouped send/recv call.
+  auto exchange = [&](int x) -> int {
+    const int to = (rank + x) % world, from = (rank - x + world) % world;
+    char* const dst = kbuf((x - 1) % depth);
+    int e = nccl.GroupStart();
+    if (e == 0) e = nccl.Send(K, bytes, kNcclUint8, to, nccl_comm, st->s_ring);
+    if (e == 0) e = nccl.Send(V, bytes, kNcclUint8, to, nccl_comm, st->s_ring);
+    if (e == 0) e = nccl.Recv(dst, bytes, kNcclUint8, from, nccl_comm, st->s_ring);
+    if (e == 0) e = nccl.Recv(dst + L.shard_bytes, bytes, kNcclUint8, from, nccl_comm, st->s_ring);
+    const int g = nccl.GroupEnd();
+    if (e == 0) e = g;
+    if (e != 0) return FA_ERR_NCCL;
+    FA_CUDA_TRY(cudaEventRecord(st->ev_ring_recv[x], st->s_ring));
+    return FA_OK;
+  };
+  // K, V (and the workspace, whatever used it last) are ready where the caller's stream stands now
+  FA_CUDA_TRY(cudaEventRecord(st->ev_ring_ready, s));
+  FA_CUDA_TRY(cudaStreamWaitEvent(st->s_ring, st->ev_ring_ready, 0));
+  for (int x = 1; x <= depth && x < world; ++x)
+    if ((rc = exchange(x)) != FA_OK) return rc;
+  // step 0 needs no exchange: the first exchanges run under it
+  if ((rc = fa_forward_partial(Q, K, V, o_acc, m, l, B, H, n, n, D, scale, 1, 0, nullptr, stream)) != FA_OK) return rc;
+  for (int x = 1; x < world; ++x) {
+    char* const src = kbuf((x - 1) % depth);
+    FA_CUDA_TRY(cudaStreamWaitEvent(s, st->ev_ring_recv[x], 0));
+    if ((rc = fa_forward_partial(Q, src, src + L.shard_bytes, o_acc, m, l, B, H, n, n, D, scale, 0, x == world - 1 ? 1 : 0,
+                                 O, stream)) != FA_OK)
+      return rc;
+    if (x + depth < world) {  // the buffer step x just read is the one exchange x + depth fills
+      FA_CUDA_TRY(cudaEventRecord(st->ev_ring_step[x], s));
+      FA_CUDA_TRY(cudaStreamWaitEvent(st->s_ring, st->ev_ring_step[x], 0));
+      if ((rc = exchange(x + depth)) != FA_OK) return rc;
+    }
+  }
+  return FA_OK;
 }
 
 int fa_forward_cross(const void* Q, const void* K, const void* V, float* O, int B, int H, int Nq, int Nkv, int D,
@@ -546,19 +852,19 @@ int fa_forward_host(const void* Q, const void* K, const void* V, void* O, int B,
   for (int c = 0; c < nchunk; ++c) {
     const long long u0 = bh * c / nchunk, u1 = bh * (c + 1) / nchunk;
     const size_t off = static_cast<size_t>(u0) * unit, len = static_cast<size_t>(u1 - u0) * unit;
-    FA_CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(dq) + off, static_cast<const char*>(Q) + off, len, cudaMemcpyHostToDevice, st->s_in));
-    FA_CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(dk) + off, static_cast<const char*>(K) + off, len, cudaMemcpyHostToDevice, st->s_in));
-    FA_CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(dv) + off, static_cast<const char*>(V) + off, len, cudaMemcpyHostToDevice, st->s_in));
-    FA_CUDA_TRY(cudaEventRecord(st->ev_in[c], st->s_in));
-    FA_CUDA_TRY(cudaStreamWaitEvent(st->s_run, st->ev_in[c], 0));
+    FA_PIPE_TRY(st, cudaMemcpyAsync(static_cast<char*>(dq) + off, static_cast<const char*>(Q) + off, len, cudaMemcpyHostToDevice, st->s_in));
+    FA_PIPE_TRY(st, cudaMemcpyAsync(static_cast<char*>(dk) + off, static_cast<const char*>(K) + off, len, cudaMemcpyHostToDevice, st->s_in));
+    FA_PIPE_TRY(st, cudaMemcpyAsync(static_cast<char*>(dv) + off, static_cast<const char*>(V) + off, len, cudaMemcpyHostToDevice, st->s_in));
+    FA_PIPE_TRY(st, cudaEventRecord(st->ev_in[c], st->s_in));
+    FA_PIPE_TRY(st, cudaStreamWaitEvent(st->s_run, st->ev_in[c], 0));
     if ((rc = fa_forward(static_cast<char*>(dq) + off, static_cast<char*>(dk) + off, static_cast<char*>(dv) + off,
                          static_cast<char*>(dout) + off, 1, static_cast<int>(u1 - u0), N, D, scale, st->s_run)) != FA_OK) {
       host_pipe_drain(st);
       return rc;
     }
-    FA_CUDA_TRY(cudaEventRecord(st->ev_run[c], st->s_run));
-    FA_CUDA_TRY(cudaStreamWaitEvent(st->s_out, st->ev_run[c], 0));
-    FA_CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(O) + off, static_cast<char*>(dout) + off, len, cudaMemcpyDeviceToHost, st->s_out));
+    FA_PIPE_TRY(st, cudaEventRecord(st->ev_run[c], st->s_run));
+    FA_PIPE_TRY(st, cudaStreamWaitEvent(st->s_out, st->ev_run[c], 0));
+    FA_PIPE_TRY(st, cudaMemcpyAsync(static_cast<char*>(O) + off, static_cast<char*>(dout) + off, len, cudaMemcpyDeviceToHost, st->s_out));
   }
   return host_pipe_drain(st);
 }
@@ -581,8 +887,8 @@ int gemm_fused_epilogue_host(const void* A, const void* Bm, const float* bias, c
   if (bias != nullptr && (rc = scratch_get(st, 4, biasb, &dbias)) != FA_OK) return rc;
   if (residual != nullptr && (rc = scratch_get(st, 2, cb, &dres)) != FA_OK) return rc;
   // B and bias are shared by every row block and go first; then row blocks of A / residual / C are pipelined
-  FA_CUDA_TRY(cudaMemcpyAsync(db, Bm, bb, cudaMemcpyHostToDevice, st->s_in));
-  if (bias != nullptr) FA_CUDA_TRY(cudaMemcpyAsync(dbias, bias, biasb, cudaMemcpyHostToDevice, st->s_in));
+  FA_PIPE_TRY(st, cudaMemcpyAsync(db, Bm, bb, cudaMemcpyHostToDevice, st->s_in));
+  if (bias != nullptr) FA_PIPE_TRY(st, cudaMemcpyAsync(dbias, bias, biasb, cudaMemcpyHostToDevice, st->s_in));
   const long long row_blocks = (static_cast<long long>(M) + 255) / 256;  // chunks are whole 256-row output tiles
   const int nchunk = host_chunks(ab + 2 * cb, row_blocks);
   for (int c = 0; c < nchunk; ++c) {
@@ -591,13 +897,13 @@ int gemm_fused_epilogue_host(const void* A, const void* Bm, const float* bias, c
     if (r1 > M) r1 = M;
     const int rows = static_cast<int>(r1 - r0);
     const size_t a_off = static_cast<size_t>(r0) * K * 2, c_off = static_cast<size_t>(r0) * N * 4;
-    FA_CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(da) + a_off, static_cast<const char*>(A) + a_off,
+    FA_PIPE_TRY(st, cudaMemcpyAsync(static_cast<char*>(da) + a_off, static_cast<const char*>(A) + a_off,
                                 static_cast<size_t>(rows) * K * 2, cudaMemcpyHostToDevice, st->s_in));
     if (residual != nullptr)
-      FA_CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(dres) + c_off, reinterpret_cast<const char*>(residual) + c_off,
+      FA_PIPE_TRY(st, cudaMemcpyAsync(static_cast<char*>(dres) + c_off, reinterpret_cast<const char*>(residual) + c_off,
                                   static_cast<size_t>(rows) * N * 4, cudaMemcpyHostToDevice, st->s_in));
-    FA_CUDA_TRY(cudaEventRecord(st->ev_in[c], st->s_in));
-    FA_CUDA_TRY(cudaStreamWaitEvent(st->s_run, st->ev_in[c], 0));
+    FA_PIPE_TRY(st, cudaEventRecord(st->ev_in[c], st->s_in));
+    FA_PIPE_TRY(st, cudaStreamWaitEvent(st->s_run, st->ev_in[c], 0));
     rc = gemm_fused_epilogue(static_cast<char*>(da) + a_off, db, static_cast<const float*>(dbias),
                              residual != nullptr ? reinterpret_cast<const float*>(static_cast<char*>(dres) + c_off) : nullptr,
                              reinterpret_cast<float*>(static_cast<char*>(dc) + c_off), rows, N, K, st->s_run);
@@ -605,9 +911,9 @@ int gemm_fused_epilogue_host(const void* A, const void* Bm, const float* bias, c
       host_pipe_drain(st);
       return rc;
     }
-    FA_CUDA_TRY(cudaEventRecord(st->ev_run[c], st->s_run));
-    FA_CUDA_TRY(cudaStreamWaitEvent(st->s_out, st->ev_run[c], 0));
-    FA_CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<char*>(C) + c_off, static_cast<char*>(dc) + c_off,
+    FA_PIPE_TRY(st, cudaEventRecord(st->ev_run[c], st->s_run));
+    FA_PIPE_TRY(st, cudaStreamWaitEvent(st->s_out, st->ev_run[c], 0));
+    FA_PIPE_TRY(st, cudaMemcpyAsync(reinterpret_cast<char*>(C) + c_off, static_cast<char*>(dc) + c_off,
                                 static_cast<size_t>(rows) * N * 4, cudaMemcpyDeviceToHost, st->s_out));
   }
   return host_pipe_drain(st);
@@ -630,16 +936,16 @@ int softmax_rows_host(const float* X, float* P, int rows, int N) {
     const long long r0 = static_cast<long long>(rows) * c / nchunk, r1 = static_cast<long long>(rows) * (c + 1) / nchunk;
     const size_t off = static_cast<size_t>(r0) * pitch, len = static_cast<size_t>(r1 - r0) * pitch;
     float* const dchunk = reinterpret_cast<float*>(static_cast<char*>(dx) + off);
-    FA_CUDA_TRY(cudaMemcpyAsync(dchunk, reinterpret_cast<const char*>(X) + off, len, cudaMemcpyHostToDevice, st->s_in));
-    FA_CUDA_TRY(cudaEventRecord(st->ev_in[c], st->s_in));
-    FA_CUDA_TRY(cudaStreamWaitEvent(st->s_run, st->ev_in[c], 0));
+    FA_PIPE_TRY(st, cudaMemcpyAsync(dchunk, reinterpret_cast<const char*>(X) + off, len, cudaMemcpyHostToDevice, st->s_in));
+    FA_PIPE_TRY(st, cudaEventRecord(st->ev_in[c], st->s_in));
+    FA_PIPE_TRY(st, cudaStreamWaitEvent(st->s_run, st->ev_in[c], 0));
     if ((rc = softmax_rows(dchunk, dchunk, static_cast<int>(r1 - r0), N, st->s_run)) != FA_OK) {
       host_pipe_drain(st);
       return rc;
     }
-    FA_CUDA_TRY(cudaEventRecord(st->ev_run[c], st->s_run));
-    FA_CUDA_TRY(cudaStreamWaitEvent(st->s_out, st->ev_run[c], 0));
-    FA_CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<char*>(P) + off, dchunk, len, cudaMemcpyDeviceToHost, st->s_out));
+    FA_PIPE_TRY(st, cudaEventRecord(st->ev_run[c], st->s_run));
+    FA_PIPE_TRY(st, cudaStreamWaitEvent(st->s_out, st->ev_run[c], 0));
+    FA_PIPE_TRY(st, cudaMemcpyAsync(reinterpret_cast<char*>(P) + off, dchunk, len, cudaMemcpyDeviceToHost, st->s_out));
   }
   return host_pipe_drain(st);
 }
@@ -668,6 +974,38 @@ int fa_last_debug(unsigned int* words, int n) {
 }
 
 unsigned long long fa_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int fa_plan_segments(int B, int H, int Nq, int Nkv, int sms, int* out, int max_segments) {
+  if (B <= 0 || H <= 0 || Nq <= 0 || Nkv <= 0 || sms <= 0) return FA_ERR_BAD_SHAPE;
+  FaParams p{};
+  p.nq = Nq;
+  p.nkv = Nkv;
+  p.q_blocks = (Nq + 255) / 256;
+  const long long items = static_cast<long long>(B) * H * p.q_blocks;
+  if (items > 0x7fffffffll) return FA_ERR_BAD_SHAPE;
+  const int nkv_tiles = (Nkv + 127) / 128;
+  const FaPlan plan = fa_plan(items, nkv_tiles, sms, true);
+  p.items_full = plan.items_full;
+  p.tail_items = plan.tail_items;
+  p.tail_ctas = plan.tail_ctas;
+  int n = 0;
+  for (int cta = 0; cta < plan.items_full + plan.tail_ctas; ++cta) {
+    FaSegment seg;
+    for (int si = 0; fa_segment(p, nkv_tiles, cta, si, seg); ++si, ++n) {
+      if (out != nullptr && n < max_segments) {
+        int* row = out + static_cast<size_t>(n) * 6;
+        row[0] = cta; row[1] = seg.item; row[2] = seg.kv0; row[3] = seg.kv1; row[4] = seg.slot; row[5] = seg.tail_item;
+      }
+    }
+  }
+  return n;
+}
+
+int fa_map_cache_stats(unsigned long long* hits, unsigned long long* misses) {
+  if (hits != nullptr) *hits = g_map_hits.load(std::memory_order_relaxed);
+  if (misses != nullptr) *misses = g_map_misses.load(std::memory_order_relaxed);
+  return kMapCacheEntries;
+}
 
 #ifdef FA_TRACE
 void fa_trace_config(long long* device_buf, int cta) {

@@ -44,6 +44,14 @@ struct FaParams {
   float* o_f32;      // FA_MODE_F32: [bh, nq, D] normalised;  FA_MODE_STATE: un-normalised O_acc
   float* m_state;    // FA_MODE_STATE: [bh, nq]  running max of scale*s (natural-log domain)
   float* l_state;    // FA_MODE_STATE: [bh, nq]
+  // Work decomposition (see FaSegment): an ITEM is one 256-row query block of one (b,h) against all K/V tiles.
+  // CTAs [0, items_full) own one whole item each; the remaining `tail_items` items -- the partial last wave --
+  // are cut along K/V into `tail_ctas` equal spans of key tiles, one per CTA, and merged through `ws`.
+  int items_full;
+  int tail_items;
+  int tail_ctas;
+  float* ws;               // tail_ctas * 2 slots of (D + 2) * 256 floats: un-normalised O, row max, row sum
+  unsigned int* ws_count;  // [tail_items] arrival counters, zero before the launch
   DebugChannel dbg;
 #ifdef FA_TRACE
   long long* trace;  // [6 roles][64 iterations][8 points]
@@ -126,6 +134,79 @@ static_assert(kSplitGroups >= 1 && kSplitGroups <= 7, "first publication covers 
 #define FA_TRACE_POINT(role, j, k) do { } while (0)
 #endif
 
+// One unit of work of a CTA: key tiles [kv0, kv1) of item `item`.  A whole item has slot = -1 and takes the ordinary
+// epilogue.  A partial one parks its un-normalised (O, m, l) in workspace slot `slot` of its CTA (0: the span starts
+// inside this item, 1: it started in an earlier item) and bumps the item's counter; the CTA that arrives last merges
+// all parts in span order (deterministic whichever CTA that is) and writes the output.  This is the "stream-K" cut
+// of the LAST WAVE only: 512 items on 148 SMs take 3.46 item-times instead of 4, which is what head-sharding
+// BASELINE config 3 over 8 GPUs (32 (b,h) per GPU) needs to scale.
+struct FaSegment {
+  int item;      // global item index = bh * q_blocks + qblk
+  int kv0, kv1;  // key-tile range
+  int slot;      // -1 = whole item
+  int tail_item; // index into ws_count (partial only)
+};
+
+// All of this is 32-bit arithmetic (a 64-bit division is a subroutine call that spills the caller's registers); the
+// host only cuts the tail when (tail_items * nkv_tiles + 1) * tail_ctas < 2^31 (fa_plan).
+__host__ __device__ __forceinline__ int fa_span_begin(const FaParams& p, int nkv_tiles, int t) {
+  return static_cast<int>(static_cast<unsigned>(t) * static_cast<unsigned>(p.tail_items * nkv_tiles) /
+                          static_cast<unsigned>(p.tail_ctas));
+}
+// tail CTA owning iteration x of the tail iteration space: largest t with span_begin(t) <= x
+__host__ __device__ __forceinline__ int fa_span_owner(const FaParams& p, int nkv_tiles, int x) {
+  const unsigned T = static_cast<unsigned>(p.tail_items * nkv_tiles);
+  return static_cast<int>((static_cast<unsigned>(x + 1) * static_cast<unsigned>(p.tail_ctas) + T - 1u) / T) - 1;
+}
+__host__ __device__ __forceinline__ bool fa_segment(const FaParams& p, int nkv_tiles, int cta, int idx, FaSegment& s) {
+  if (cta < p.items_full) {
+    if (idx != 0) return false;
+    s.item = cta; s.kv0 = 0; s.kv1 = nkv_tiles; s.slot = -1; s.tail_item = 0;
+    return true;
+  }
+  const int t = cta - p.items_full;
+  const int a = fa_span_begin(p, nkv_tiles, t), b = fa_span_begin(p, nkv_tiles, t + 1);
+  const int li = static_cast<int>(static_cast<unsigned>(a) / static_cast<unsigned>(nkv_tiles)) + idx;
+  const int i0 = li * nkv_tiles;
+  if (i0 >= b) return false;
+  const int lo = a > i0 ? a : i0, hi = b < i0 + nkv_tiles ? b : i0 + nkv_tiles;
+  s.item = p.items_full + li;
+  s.kv0 = lo - i0;
+  s.kv1 = hi - i0;
+  s.tail_item = li;
+  s.slot = (s.kv0 == 0 && s.kv1 == nkv_tiles) ? -1 : (a >= i0 ? 0 : 1);
+  return true;
+}
+
+// (Re-)arms every mbarrier of the CTA; one thread, between two CTA-wide barriers.  Layout as in the kernel:
+// q_full[2], kv_full[S], kv_empty[S], s_full[2], p_full[2][chunks], stats_full[2], o_full[2], l_full[2].
+template <int D>
+__device__ __forceinline__ void fa_init_barriers(uint64_t* bars, bool reinit) {
+  using Cfg = FaCfg<D>;
+  if (reinit)
+    for (int b = 0; b < Cfg::kNumBars; ++b) mbar_inval(&bars[b]);
+  uint64_t* b = bars;
+  for (int i = 0; i < 2 + 2 * Cfg::kStages + 2; ++i) mbar_init(b++, 1);  // q_full, kv_full, kv_empty, s_full
+  // softmax / correction warps arrive once per warp (lane 0 after __syncwarp): count 4.  P chunk 0 also collects the
+  // correction warps: "P ready" and "O rescaled" are one wait for the MMA warp
+  for (int i = 0; i < 2; ++i)
+    for (int c = 0; c < Cfg::kPChunks; ++c) mbar_init(b++, c == 0 ? 8 : 4);
+  for (int i = 0; i < 2; ++i) mbar_init(b++, 4);  // stats_full
+  for (int i = 0; i < 2; ++i) mbar_init(b++, 1);  // o_full
+  for (int i = 0; i < 2; ++i) mbar_init(b++, 4);  // l_full
+  fence_mbar_init();
+}
+// Between two segments of a tail CTA: every role has finished the previous segment (the epilogue's TMA store has read
+// its staging tile), and the barriers start again at phase 0.  Whole-item CTAs never come here.
+template <int D>
+__device__ __forceinline__ void fa_segment_boundary(uint64_t* bars, int warp, int lane) {
+  tc_fence_before();
+  named_bar_sync(2, 14 * 32);  // the 14 working warps; warps 14 and 15 only hold registers for the others
+  if (warp == 12 && lane == 0) fa_init_barriers<D>(bars, true);
+  named_bar_sync(2, 14 * 32);
+  tc_fence_after();
+}
+
 template <int D>
 __global__ void __launch_bounds__(512, 1)
 fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
@@ -147,38 +228,22 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
   uint64_t* const stats_full = p_full + 2 * Cfg::kPChunks;  // [2]  softmax -> correction : factors
   uint64_t* const o_full = stats_full + 2;                // [2]  MMA -> correction : last PV done
   uint64_t* const l_full = o_full + 2;                    // [2]  softmax -> correction : final l
-  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(smem + Cfg::kOffTmem);
+  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(smem + Cfg::kOffTmem);  // [0] TMEM base, [1] merge verdict
 
   const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int qblk = blockIdx.x % p.q_blocks;
-  const int bh = blockIdx.x / p.q_blocks;
-  const int q0 = qblk * 256;
-  const int ntile = (q0 + 128 < p.nq) ? 2 : 1;
-  const int nkv_tiles = (p.nkv + Cfg::kKT - 1) / Cfg::kKT;
   const DebugChannel dbg = p.dbg;
+  // per-role copies of the cheap common values: kept across the setmaxnreg boundaries they would be spilled
+#define FA_ROLE_COMMON()                                            \
+  const int lane = threadIdx.x & 31;                                \
+  const int cta = blockIdx.x;                                       \
+  const int nkv_tiles = (p.nkv + Cfg::kKT - 1) / Cfg::kKT
 
   // ------------------------------- one-time setup -------------------------------------
-  if (warp == 12 && lane == 0) {
+  if (threadIdx.x == 12 * 32) {
     if ((smem_u32(smem) & 1023u) != 0u) wait_timeout_trap(dbg, 0xA11u, 0, smem_u32(smem));
-    mbar_init(&q_full[0], 1);
-    mbar_init(&q_full[1], 1);
-    for (int s = 0; s < Cfg::kStages; ++s) {
-      mbar_init(&kv_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      // softmax / correction warps arrive once per warp (lane 0 after __syncwarp): count 4
-      mbar_init(&s_full[i], 1);
-      // chunk 0 also collects the correction warps: "P ready" and "O rescaled" are one wait for the MMA warp
-      for (int c = 0; c < Cfg::kPChunks; ++c) mbar_init(&p_full[i * Cfg::kPChunks + c], c == 0 ? 8 : 4);
-      mbar_init(&stats_full[i], 4);
-      mbar_init(&o_full[i], 1);
-      mbar_init(&l_full[i], 4);
-    }
-    fence_mbar_init();
+    fa_init_barriers<D>(bars, false);
   }
-  if (warp == 13 && lane == 0) {
+  if (threadIdx.x == 13 * 32) {
     prefetch_tensormap(&mapQ);
     prefetch_tensormap(&mapK);
     prefetch_tensormap(&mapV);
@@ -196,18 +261,25 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
   if (warp < 8) {
     // =============================== softmax warpgroups ===============================
     setmaxnreg_inc<192>();
+    FA_ROLE_COMMON();
     const int i = warp >> 2;  // Q tile handled by this warpgroup
-    if (i < ntile) {
-      const int row = (warp & 3) * 32 + lane;
-      const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
-      const uint32_t t_s = tmem_base + lane_base + (i == 0 ? Cfg::kColS0 : Cfg::kColS1);
-      float c = p.scale_log2;
-      const bool neg_scale = c < 0.f;  // max over scale*s == -|scale| * min(s): fold the sign into s
-      if (neg_scale) c = -c;
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t t_s = tmem_base + lane_base + (i == 0 ? Cfg::kColS0 : Cfg::kColS1);
+    float c = p.scale_log2;
+    const bool neg_scale = c < 0.f;  // max over scale*s == -|scale| * min(s): fold the sign into s
+    if (neg_scale) c = -c;
+    FaSegment seg;
+    for (int si = 0; fa_segment(p, nkv_tiles, cta, si, seg); ++si) {
+      if (si > 0) fa_segment_boundary<D>(bars, warp, lane);
+      const int q0 = (seg.item % p.q_blocks) * 256;
+      const int ntile = (q0 + 128 < p.nq) ? 2 : 1;
+      if (i >= ntile) continue;
+      const int n_it = seg.kv1 - seg.kv0;
       float m_used = -INFINITY;  // running max of (sign-folded) raw scores the exponent refers to
       float l = 0.f;
 
-      for (int j = 0; j < nkv_tiles; ++j) {
+      for (int j = 0; j < n_it; ++j) {
         if ((warp & 3) == 0 && lane == 0) FA_TRACE_POINT(i, j, 0);
         mbar_wait(&s_full[i], j & 1, dbg, SITE_SM_SFULL, j);
         tc_fence_after();
@@ -224,8 +296,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < 128; ++k) s[k] = -s[k];
         }
-        if (j == nkv_tiles - 1 && (p.nkv & 127) != 0) {
-          const int valid = p.nkv - j * 128;  // keys beyond nkv were zero-filled by TMA: mask them
+        if (seg.kv0 + j == nkv_tiles - 1 && (p.nkv & 127) != 0) {
+          const int valid = p.nkv - (nkv_tiles - 1) * 128;  // keys beyond nkv were zero-filled by TMA: mask them
 #pragma unroll
           for (int k = 0; k < 128; ++k)
             if (k >= valid) s[k] = -INFINITY;
@@ -347,11 +419,11 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
 
       // final statistics for the epilogue
       sum_smem[i * 128 + row] = l;
-      if (p.mode == FA_MODE_STATE) {
+      if (p.mode == FA_MODE_STATE || seg.slot >= 0) {
         // fac_smem doubles as the final-max slot; the correction WG has consumed its last factor
         // once the last phase of p_full[chunk 0] (which its warps also arrive on) has completed.
-        mbar_wait(&p_full[i * Cfg::kPChunks], (nkv_tiles - 1) & 1, dbg, SITE_SM_CORR, i);
-        fac_smem[i * 128 + row] = neg_scale ? -m_used : m_used;  // raw-score max, true sign
+        mbar_wait(&p_full[i * Cfg::kPChunks], (n_it - 1) & 1, dbg, SITE_SM_CORR, i);
+        fac_smem[i * 128 + row] = m_used;  // max of the sign-folded raw scores
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&l_full[i]);
@@ -359,132 +431,224 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
   } else if (warp < 12) {
     // ========================= correction + epilogue warpgroup ========================
     setmaxnreg_dec<80>();
+    FA_ROLE_COMMON();
     const int wq = warp & 3;
     const int row = wq * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(wq * 32) << 16;
+    const float c_abs = fabsf(p.scale_log2);
+    constexpr int kSlotFloats = (D + 2) * 256;  // workspace slot: O as [D/4][256 rows] float4, then m[256], l[256]
+    FaSegment seg;
+    for (int si = 0; fa_segment(p, nkv_tiles, cta, si, seg); ++si) {
+      if (si > 0) {
+        if (warp == 8 && lane == 0) tma_store_wait_read<0>();  // the staging tiles become Q tiles again
+        fa_segment_boundary<D>(bars, warp, lane);
+      }
+      const int bh = seg.item / p.q_blocks;
+      const int q0 = (seg.item % p.q_blocks) * 256;
+      const int ntile = (q0 + 128 < p.nq) ? 2 : 1;
+      const int n_it = seg.kv1 - seg.kv0;
 
-    // j == 0: nothing to rescale (PV(0) overwrites O); the arrival only balances the barrier count
-    if (lane == 0)
-      for (int i = 0; i < ntile; ++i) mbar_arrive(&p_full[i * Cfg::kPChunks]);
-    for (int j = 1; j < nkv_tiles; ++j) {
-      for (int i = 0; i < ntile; ++i) {
-        mbar_wait(&stats_full[i], (j - 1) & 1, dbg, SITE_CO_STATS, j);
-        if (warp == 8 && lane == 0) FA_TRACE_POINT(2 + i, j, 0);
-        const float fac = fac_smem[i * 128 + row];
-        if (__any_sync(0xffffffffu, fac != 1.f)) {
+      // j == 0: nothing to rescale (PV(0) overwrites O); the arrival only balances the barrier count
+      if (lane == 0)
+        for (int i = 0; i < ntile; ++i) mbar_arrive(&p_full[i * Cfg::kPChunks]);
+      for (int j = 1; j < n_it; ++j) {
+        for (int i = 0; i < ntile; ++i) {
+          mbar_wait(&stats_full[i], (j - 1) & 1, dbg, SITE_CO_STATS, j);
+          if (warp == 8 && lane == 0) FA_TRACE_POINT(2 + i, j, 0);
+          const float fac = fac_smem[i * 128 + row];
+          if (__any_sync(0xffffffffu, fac != 1.f)) {
+            tc_fence_after();
+            const uint32_t t_o = tmem_base + lane_base + (i == 0 ? Cfg::kColO0 : Cfg::kColO1);
+#pragma unroll
+            for (int cc = 0; cc < D / 32; ++cc) {
+              uint32_t o[32];
+              tmem_ld_x32(t_o + cc * 32, o);
+              tmem_wait_ld();
+#pragma unroll
+              for (int k = 0; k < 32; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * fac);
+              tmem_st_x32(t_o + cc * 32, o);
+            }
+            tmem_wait_st();
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[i * Cfg::kPChunks]);
+          if (warp == 8 && lane == 0) FA_TRACE_POINT(2 + i, j, 1);
+        }
+      }
+
+      // ---- a partial segment parks its state; the part that arrives last merges them all ----
+      if (seg.slot >= 0) {
+        float* const slot = p.ws + (static_cast<size_t>(cta - p.items_full) * 2 + seg.slot) * kSlotFloats;
+        for (int i = 0; i < ntile; ++i) {
+          mbar_wait(&l_full[i], 0, dbg, SITE_CO_LFULL, i);
+          mbar_wait(&o_full[i], 0, dbg, SITE_CO_OFULL, i);
           tc_fence_after();
           const uint32_t t_o = tmem_base + lane_base + (i == 0 ? Cfg::kColO0 : Cfg::kColO1);
-#pragma unroll
+          const int ri = i * 128 + row;
+          __stcg(slot + D * 256 + ri, fac_smem[ri]);
+          __stcg(slot + D * 256 + 256 + ri, sum_smem[ri]);
+#pragma unroll 1
           for (int cc = 0; cc < D / 32; ++cc) {
             uint32_t o[32];
             tmem_ld_x32(t_o + cc * 32, o);
             tmem_wait_ld();
 #pragma unroll
-            for (int k = 0; k < 32; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * fac);
-            tmem_st_x32(t_o + cc * 32, o);
+            for (int k4 = 0; k4 < 8; ++k4)
+              __stcg(reinterpret_cast<float4*>(slot) + (cc * 8 + k4) * 256 + ri,
+                     make_float4(__uint_as_float(o[4 * k4]), __uint_as_float(o[4 * k4 + 1]),
+                                 __uint_as_float(o[4 * k4 + 2]), __uint_as_float(o[4 * k4 + 3])));
+          }
+        }
+        // parts of this item: tail CTAs part_first..part_last; every part but the first starts its span inside
+        // the item (slot 0), the first one does so only if its span begins exactly at the item
+        const int item_begin = seg.tail_item * nkv_tiles;
+        const int part_first = fa_span_owner(p, nkv_tiles, item_begin);
+        const int part_last = fa_span_owner(p, nkv_tiles, item_begin + nkv_tiles - 1);
+        const int first_slot = fa_span_begin(p, nkv_tiles, part_first) == item_begin ? 0 : 1;
+        __threadfence();
+        named_bar_sync(1, 128);
+        if (warp == 8 && lane == 0) {
+          const unsigned int arrived = atomicAdd(p.ws_count + seg.tail_item, 1u);
+          tmem_slot[1] = (arrived == static_cast<unsigned int>(part_last - part_first)) ? 1u : 0u;
+          __threadfence();
+        }
+        named_bar_sync(1, 128);
+        if (tmem_slot[1] == 0u) continue;  // another CTA finishes this item
+        // Last to arrive: reduce all parts, in span order (the same arithmetic whichever CTA does it), into this
+        // CTA's own O accumulator and statistics, then fall through to the ordinary epilogue.
+        for (int i = 0; i < ntile; ++i) {
+          const uint32_t t_o = tmem_base + lane_base + (i == 0 ? Cfg::kColO0 : Cfg::kColO1);
+          const int ri = i * 128 + row;
+          float m_all = -INFINITY;
+          for (int t = part_first; t <= part_last; ++t) {
+            const float* const ps = p.ws + (static_cast<size_t>(t) * 2 + (t == part_first ? first_slot : 0)) * kSlotFloats;
+            m_all = fmaxf(m_all, __ldcg(ps + D * 256 + ri));
+          }
+          float l_all = 0.f;
+          for (int t = part_first; t <= part_last; ++t) {
+            const float* const ps = p.ws + (static_cast<size_t>(t) * 2 + (t == part_first ? first_slot : 0)) * kSlotFloats;
+            l_all = fmaf(__ldcg(ps + D * 256 + 256 + ri), ex2_approx((__ldcg(ps + D * 256 + ri) - m_all) * c_abs), l_all);
+          }
+#pragma unroll 1
+          for (int cc = 0; cc < D / 32; ++cc) {
+            float v[32];
+#pragma unroll
+            for (int k = 0; k < 32; ++k) v[k] = 0.f;
+            for (int t = part_first; t <= part_last; ++t) {
+              const float* const ps = p.ws + (static_cast<size_t>(t) * 2 + (t == part_first ? first_slot : 0)) * kSlotFloats;
+              const float w = ex2_approx((__ldcg(ps + D * 256 + ri) - m_all) * c_abs);
+#pragma unroll
+              for (int k4 = 0; k4 < 8; ++k4) {
+                const float4 a = __ldcg(reinterpret_cast<const float4*>(ps) + (cc * 8 + k4) * 256 + ri);
+                v[4 * k4 + 0] = fmaf(a.x, w, v[4 * k4 + 0]);
+                v[4 * k4 + 1] = fmaf(a.y, w, v[4 * k4 + 1]);
+                v[4 * k4 + 2] = fmaf(a.z, w, v[4 * k4 + 2]);
+                v[4 * k4 + 3] = fmaf(a.w, w, v[4 * k4 + 3]);
+              }
+            }
+            tmem_st_x32(t_o + cc * 32, reinterpret_cast<const uint32_t*>(v));
           }
           tmem_wait_st();
+          sum_smem[ri] = l_all;  // read back below by this same thread
+          fac_smem[ri] = m_all;
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[i * Cfg::kPChunks]);
-        if (warp == 8 && lane == 0) FA_TRACE_POINT(2 + i, j, 1);
       }
-    }
 
-    // ---- epilogue: O / l -> output ----
-    for (int i = 0; i < ntile; ++i) {
-      mbar_wait(&l_full[i], 0, dbg, SITE_CO_LFULL, i);
-      mbar_wait(&o_full[i], 0, dbg, SITE_CO_OFULL, i);
-      tc_fence_after();
-      const uint32_t t_o = tmem_base + lane_base + (i == 0 ? Cfg::kColO0 : Cfg::kColO1);
-      const int grow = q0 + i * 128 + row;  // query row inside this (b,h)
-      const bool row_ok = grow < p.nq;
-      float l_new = sum_smem[i * 128 + row];
-      float o_scale = 1.f;      // factor applied to this step's un-normalised O
-      float acc_scale = 0.f;    // factor applied to the carried O_acc (STATE mode)
-      bool emit_f16 = (p.mode == FA_MODE_F16);
-      bool emit_f32 = (p.mode == FA_MODE_F32);
-      bool emit_state = false;
-      const size_t row_index = static_cast<size_t>(bh) * p.nq + grow;
-      if (p.mode == FA_MODE_STATE) {
-        // Merge (O, m, l) of this K/V shard into the carried state: the reference's tile-to-tile
-        // rule, Streaming_FlashAttention_Forward_Kernel/flashattn_streaming_16x16.cu:247-261.
-        const float scale_ln = p.scale_log2 * 0.6931471805599453f;
-        const float m_new_s = fac_smem[i * 128 + row] * scale_ln;  // max of scale*s for this shard
-        float m_acc = -INFINITY, l_acc = 0.f;
-        if (!p.is_first && row_ok) {
-          m_acc = p.m_state[row_index];
-          l_acc = p.l_state[row_index];
-        }
-        const float m_tot = fmaxf(m_acc, m_new_s);
-        acc_scale = (m_acc == -INFINITY) ? 0.f : ex2_approx((m_acc - m_tot) * 1.4426950408889634f);
-        o_scale = ex2_approx((m_new_s - m_tot) * 1.4426950408889634f);
-        const float l_tot = l_acc * acc_scale + l_new * o_scale;
-        if (p.is_last) {
-          emit_f16 = true;
-          const float inv = 1.f / l_tot;
-          o_scale *= inv;
-          acc_scale *= inv;
-        } else {
-          emit_state = true;
-          if (row_ok) {
-            p.m_state[row_index] = m_tot;
-            p.l_state[row_index] = l_tot;
+      // ---- epilogue: O / l -> output ----
+      for (int i = 0; i < ntile; ++i) {
+        mbar_wait(&l_full[i], 0, dbg, SITE_CO_LFULL, i);
+        mbar_wait(&o_full[i], 0, dbg, SITE_CO_OFULL, i);
+        tc_fence_after();
+        const float l_new = sum_smem[i * 128 + row];
+        const float m_fold = fac_smem[i * 128 + row];  // meaningful in STATE mode and after a merge
+        const uint32_t t_o = tmem_base + lane_base + (i == 0 ? Cfg::kColO0 : Cfg::kColO1);
+        const int grow = q0 + i * 128 + row;  // query row inside this (b,h)
+        const bool row_ok = grow < p.nq;
+        float o_scale = 1.f;      // factor applied to this step's un-normalised O
+        float acc_scale = 0.f;    // factor applied to the carried O_acc (STATE mode)
+        bool emit_f16 = (p.mode == FA_MODE_F16);
+        bool emit_f32 = (p.mode == FA_MODE_F32);
+        bool emit_state = false;
+        const size_t row_index = static_cast<size_t>(bh) * p.nq + grow;
+        if (p.mode == FA_MODE_STATE) {
+          // Merge (O, m, l) of this K/V shard into the carried state: the reference's tile-to-tile
+          // rule, Streaming_FlashAttention_Forward_Kernel/flashattn_streaming_16x16.cu:247-261.
+          const float m_new_s = m_fold * (c_abs * 0.6931471805599453f);  // max of scale*s for this shard
+          float m_acc = -INFINITY, l_acc = 0.f;
+          if (!p.is_first && row_ok) {
+            m_acc = p.m_state[row_index];
+            l_acc = p.l_state[row_index];
           }
+          const float m_tot = fmaxf(m_acc, m_new_s);
+          acc_scale = (m_acc == -INFINITY) ? 0.f : ex2_approx((m_acc - m_tot) * 1.4426950408889634f);
+          o_scale = ex2_approx((m_new_s - m_tot) * 1.4426950408889634f);
+          const float l_tot = l_acc * acc_scale + l_new * o_scale;
+          if (p.is_last) {
+            emit_f16 = true;
+            const float inv = 1.f / l_tot;
+            o_scale *= inv;
+            acc_scale *= inv;
+          } else {
+            emit_state = true;
+            if (row_ok) {
+              p.m_state[row_index] = m_tot;
+              p.l_state[row_index] = l_tot;
+            }
+          }
+        } else {
+          o_scale = 1.f / l_new;
         }
-      } else {
-        o_scale = 1.f / l_new;
-      }
-      const bool have_acc = (p.mode == FA_MODE_STATE) && !p.is_first;
-      float* const acc_row = p.o_f32 + row_index * D;
-      uint8_t* const stage = q_smem + i * Cfg::kTileBytes;  // Q tile i is dead once o_full fired
+        const bool have_acc = (p.mode == FA_MODE_STATE) && !p.is_first;
+        float* const acc_row = p.o_f32 + row_index * D;
+        uint8_t* const stage = q_smem + i * Cfg::kTileBytes;  // Q tile i is dead once o_full fired
 
 #pragma unroll
-      for (int cc = 0; cc < D / 32; ++cc) {
-        uint32_t o[32];
-        tmem_ld_x32(t_o + cc * 32, o);
-        tmem_wait_ld();
-        float v[32];
+        for (int cc = 0; cc < D / 32; ++cc) {
+          uint32_t o[32];
+          tmem_ld_x32(t_o + cc * 32, o);
+          tmem_wait_ld();
+          float v[32];
 #pragma unroll
-        for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(o[k]) * o_scale;
-        if (have_acc && row_ok) {
+          for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(o[k]) * o_scale;
+          if (have_acc && row_ok) {
 #pragma unroll
-          for (int k = 0; k < 32; k += 4) {
-            const float4 a = *reinterpret_cast<const float4*>(acc_row + cc * 32 + k);
-            v[k + 0] = fmaf(a.x, acc_scale, v[k + 0]);
-            v[k + 1] = fmaf(a.y, acc_scale, v[k + 1]);
-            v[k + 2] = fmaf(a.z, acc_scale, v[k + 2]);
-            v[k + 3] = fmaf(a.w, acc_scale, v[k + 3]);
+            for (int k = 0; k < 32; k += 4) {
+              const float4 a = *reinterpret_cast<const float4*>(acc_row + cc * 32 + k);
+              v[k + 0] = fmaf(a.x, acc_scale, v[k + 0]);
+              v[k + 1] = fmaf(a.y, acc_scale, v[k + 1]);
+              v[k + 2] = fmaf(a.z, acc_scale, v[k + 2]);
+              v[k + 3] = fmaf(a.w, acc_scale, v[k + 3]);
+            }
+          }
+          if (emit_f16) {
+            // 32 columns = 64 B = four 16-byte chunks of this row inside a 128B-swizzled box
+            uint8_t* const box = stage + (cc >> 1) * Cfg::kBoxBytes + row * 128;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 w;
+              w.x = pack_half2(v[q * 8 + 0], v[q * 8 + 1]);
+              w.y = pack_half2(v[q * 8 + 2], v[q * 8 + 3]);
+              w.z = pack_half2(v[q * 8 + 4], v[q * 8 + 5]);
+              w.w = pack_half2(v[q * 8 + 6], v[q * 8 + 7]);
+              const int chunk = (cc & 1) * 4 + q;
+              *reinterpret_cast<uint4*>(box + ((chunk ^ (row & 7)) << 4)) = w;
+            }
+          } else if ((emit_f32 || emit_state) && row_ok) {
+#pragma unroll
+            for (int k = 0; k < 32; k += 4)
+              *reinterpret_cast<float4*>(acc_row + cc * 32 + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
           }
         }
         if (emit_f16) {
-          // 32 columns = 64 B = four 16-byte chunks of this row inside a 128B-swizzled box
-          uint8_t* const box = stage + (cc >> 1) * Cfg::kBoxBytes + row * 128;
+          fence_proxy_async_smem();
+          named_bar_sync(1, 128);
+          if (warp == 8 && lane == 0) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 w;
-            w.x = pack_half2(v[q * 8 + 0], v[q * 8 + 1]);
-            w.y = pack_half2(v[q * 8 + 2], v[q * 8 + 3]);
-            w.z = pack_half2(v[q * 8 + 4], v[q * 8 + 5]);
-            w.w = pack_half2(v[q * 8 + 6], v[q * 8 + 7]);
-            const int chunk = (cc & 1) * 4 + q;
-            *reinterpret_cast<uint4*>(box + ((chunk ^ (row & 7)) << 4)) = w;
+            for (int b = 0; b < Cfg::kBoxes; ++b)
+              tma_store_3d(&mapO, stage + b * Cfg::kBoxBytes, b * 64, q0 + i * 128, bh);  // clips rows >= nq
+            tma_store_commit();
           }
-        } else if ((emit_f32 || emit_state) && row_ok) {
-#pragma unroll
-          for (int k = 0; k < 32; k += 4)
-            *reinterpret_cast<float4*>(acc_row + cc * 32 + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
-        }
-      }
-      if (emit_f16) {
-        fence_proxy_async_smem();
-        named_bar_sync(1, 128);
-        if (warp == 8 && lane == 0) {
-#pragma unroll
-          for (int b = 0; b < Cfg::kBoxes; ++b)
-            tma_store_3d(&mapO, stage + b * Cfg::kBoxBytes, b * 64, q0 + i * 128, bh);  // clips rows >= nq
-          tma_store_commit();
         }
       }
     }
@@ -498,8 +662,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
     // execute in order, which gives PV_i(j) before QK_i(j+1) (whose S overwrites P_i) for free.
     // (Two issuing warps, one per tile, were measured slower: the tiles' MMAs interleave on the pipe
     //  and lengthen each tile's S -> softmax -> P chain.)
-    setmaxnreg_dec<48>();
+    setmaxnreg_dec<64>();
     {
+      FA_ROLE_COMMON();
       constexpr uint32_t idesc_qk = umma_idesc_f16(128, 128, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_f16(128, D, 0, 1);
       const uint32_t q_addr = smem_u32(q_smem);
@@ -543,41 +708,49 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
       auto slot_of = [](int t) { return t % Cfg::kStages; };
       auto par_of = [](int t) { return (t / Cfg::kStages) & 1; };
 
-      // prologue: S_i(0) = Q_i K(0)^T
-      mbar_wait(&q_full[0], 0, dbg, SITE_MMA_QFULL, 0);
-      mbar_wait(&kv_full[slot_of(0)], par_of(0), dbg, SITE_MMA_KVFULL, 0);
-      tc_fence_after();
-      issue_qk(0, slot_of(0), ntile == 2 ? nullptr : &kv_empty[slot_of(0)]);
-      if (ntile == 2) {
-        mbar_wait(&q_full[1], 0, dbg, SITE_MMA_QFULL, 1);
-        tc_fence_after();
-        issue_qk(1, slot_of(0), &kv_empty[slot_of(0)]);
-      }
+      FaSegment seg;
+      for (int si = 0; fa_segment(p, nkv_tiles, cta, si, seg); ++si) {
+        if (si > 0) fa_segment_boundary<D>(bars, warp, lane);
+        const int q0 = (seg.item % p.q_blocks) * 256;
+        const int ntile = (q0 + 128 < p.nq) ? 2 : 1;
+        const int n_it = seg.kv1 - seg.kv0;
 
-      for (int j = 0; j < nkv_tiles; ++j) {
-        const int tv = 2 * j + 1, tk = 2 * j + 2;
-        const bool more = (j + 1 < nkv_tiles);
-        if (lane == 0) FA_TRACE_POINT(4, j, 5);
-        mbar_wait(&kv_full[slot_of(tv)], par_of(tv), dbg, SITE_MMA_KVFULL, tv);
-        if (more) mbar_wait(&kv_full[slot_of(tk)], par_of(tk), dbg, SITE_MMA_KVFULL, tk);
-        if (lane == 0) FA_TRACE_POINT(4, j, 6);
-        for (int i = 0; i < ntile; ++i) {
-          const bool last_tile = (i == ntile - 1);
-          uint64_t* const p_full_i = &p_full[i * Cfg::kPChunks];
-          if (lane == 0) FA_TRACE_POINT(4 + i, j, 0);
-          mbar_wait(&p_full_i[0], j & 1, dbg, SITE_MMA_PFULL, j);  // P chunk 0 written and O rescaled
+        // prologue: S_i(0) = Q_i K(0)^T
+        mbar_wait(&q_full[0], 0, dbg, SITE_MMA_QFULL, 0);
+        mbar_wait(&kv_full[slot_of(0)], par_of(0), dbg, SITE_MMA_KVFULL, 0);
+        tc_fence_after();
+        issue_qk(0, slot_of(0), ntile == 2 ? nullptr : &kv_empty[slot_of(0)]);
+        if (ntile == 2) {
+          mbar_wait(&q_full[1], 0, dbg, SITE_MMA_QFULL, 1);
           tc_fence_after();
-          if (lane == 0) FA_TRACE_POINT(4 + i, j, 1);
-          issue_pv_chunk(i, slot_of(tv), 0, j > 0, nullptr, nullptr);
-          mbar_wait(&p_full_i[1], j & 1, dbg, SITE_MMA_PFULL, j);
-          tc_fence_after();
-          // V(j) is released by the commit that follows its last reader; the final PV also signals o_full
-          issue_pv_chunk(i, slot_of(tv), 1, true, last_tile ? &kv_empty[slot_of(tv)] : nullptr,
-                         more ? nullptr : &o_full[i]);
-          if (lane == 0) FA_TRACE_POINT(4 + i, j, 3);
-          if (more) {
-            issue_qk(i, slot_of(tk), last_tile ? &kv_empty[slot_of(tk)] : nullptr);
-            if (lane == 0) FA_TRACE_POINT(4 + i, j, 4);
+          issue_qk(1, slot_of(0), &kv_empty[slot_of(0)]);
+        }
+
+        for (int j = 0; j < n_it; ++j) {
+          const int tv = 2 * j + 1, tk = 2 * j + 2;
+          const bool more = (j + 1 < n_it);
+          if (lane == 0) FA_TRACE_POINT(4, j, 5);
+          mbar_wait(&kv_full[slot_of(tv)], par_of(tv), dbg, SITE_MMA_KVFULL, tv);
+          if (more) mbar_wait(&kv_full[slot_of(tk)], par_of(tk), dbg, SITE_MMA_KVFULL, tk);
+          if (lane == 0) FA_TRACE_POINT(4, j, 6);
+          for (int i = 0; i < ntile; ++i) {
+            const bool last_tile = (i == ntile - 1);
+            uint64_t* const p_full_i = &p_full[i * Cfg::kPChunks];
+            if (lane == 0) FA_TRACE_POINT(4 + i, j, 0);
+            mbar_wait(&p_full_i[0], j & 1, dbg, SITE_MMA_PFULL, j);  // P chunk 0 written and O rescaled
+            tc_fence_after();
+            if (lane == 0) FA_TRACE_POINT(4 + i, j, 1);
+            issue_pv_chunk(i, slot_of(tv), 0, j > 0, nullptr, nullptr);
+            mbar_wait(&p_full_i[1], j & 1, dbg, SITE_MMA_PFULL, j);
+            tc_fence_after();
+            // V(j) is released by the commit that follows its last reader; the final PV also signals o_full
+            issue_pv_chunk(i, slot_of(tv), 1, true, last_tile ? &kv_empty[slot_of(tv)] : nullptr,
+                           more ? nullptr : &o_full[i]);
+            if (lane == 0) FA_TRACE_POINT(4 + i, j, 3);
+            if (more) {
+              issue_qk(i, slot_of(tk), last_tile ? &kv_empty[slot_of(tk)] : nullptr);
+              if (lane == 0) FA_TRACE_POINT(4 + i, j, 4);
+            }
           }
         }
       }
@@ -586,28 +759,36 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
     // ================================ TMA producer ====================================
     setmaxnreg_dec<48>();
     {
-      auto load_tile = [&](const CUtensorMap* map, uint8_t* dst, uint64_t* bar, int row0, uint64_t hint) {
-        if (elect_one()) {
-          mbar_arrive_expect_tx(bar, Cfg::kTileBytes);
+      FA_ROLE_COMMON();
+      FaSegment seg;
+      for (int si = 0; fa_segment(p, nkv_tiles, cta, si, seg); ++si) {
+        if (si > 0) fa_segment_boundary<D>(bars, warp, lane);
+        const int bh = seg.item / p.q_blocks;
+        const int q0 = (seg.item % p.q_blocks) * 256;
+        const int ntile = (q0 + 128 < p.nq) ? 2 : 1;
+        auto load_tile = [&](const CUtensorMap* map, uint8_t* dst, uint64_t* bar, int row0, uint64_t hint) {
+          if (elect_one()) {
+            mbar_arrive_expect_tx(bar, Cfg::kTileBytes);
 #pragma unroll
-          for (int b = 0; b < Cfg::kBoxes; ++b)
-            tma_load_3d(dst + b * Cfg::kBoxBytes, map, bar, b * 64, row0, bh, hint);
+            for (int b = 0; b < Cfg::kBoxes; ++b)
+              tma_load_3d(dst + b * Cfg::kBoxBytes, map, bar, b * 64, row0, bh, hint);
+          }
+          __syncwarp();
+        };
+        load_tile(&mapQ, q_smem, &q_full[0], q0, kEvictFirst);
+        const int total = 2 * (seg.kv1 - seg.kv0);
+        for (int t = 0; t < total; ++t) {
+          const int slot = t % Cfg::kStages;
+          const int par = (t / Cfg::kStages) & 1;
+          mbar_wait(&kv_empty[slot], par ^ 1, dbg, SITE_TMA_EMPTY, t);
+          load_tile((t & 1) ? &mapV : &mapK, kv_smem + slot * Cfg::kTileBytes, &kv_full[slot],
+                    (seg.kv0 + (t >> 1)) * Cfg::kKT, kEvictLast);
+          if (t == 0 && ntile == 2) load_tile(&mapQ, q_smem + Cfg::kTileBytes, &q_full[1], q0 + 128, kEvictFirst);
         }
-        __syncwarp();
-      };
-      load_tile(&mapQ, q_smem, &q_full[0], q0, kEvictFirst);
-      const int total = 2 * nkv_tiles;
-      for (int t = 0; t < total; ++t) {
-        const int slot = t % Cfg::kStages;
-        const int par = (t / Cfg::kStages) & 1;
-        mbar_wait(&kv_empty[slot], par ^ 1, dbg, SITE_TMA_EMPTY, t);
-        load_tile((t & 1) ? &mapV : &mapK, kv_smem + slot * Cfg::kTileBytes, &kv_full[slot], (t >> 1) * Cfg::kKT,
-                  kEvictLast);
-        if (t == 0 && ntile == 2) load_tile(&mapQ, q_smem + Cfg::kTileBytes, &q_full[1], q0 + 128, kEvictFirst);
       }
     }
   } else {
-    setmaxnreg_dec<48>();
+    setmaxnreg_dec<32>();
   }
 
   // ---------------------------------- teardown ----------------------------------------
@@ -615,6 +796,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   if (warp == 8) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+#undef FA_ROLE_COMMON
 }
 
 }  // namespace fa

@@ -30,8 +30,11 @@ struct DebugChannel {
   unsigned int* words;  // device-visible pointer to mapped host memory (may be null)
 };
 
+// Wall-clock bound of an mbarrier wait.  %globaltimer keeps running while the context is time-sliced out (MPS, a
+// second process on the GPU, cuda-gdb, ncu replay), so the bound is generous: it exists to turn a dead-locked launch
+// into a diagnosable trap instead of a hung GPU, not to police latency.  0 compiles the check out.
 #ifndef FA_WAIT_TIMEOUT_NS
-#define FA_WAIT_TIMEOUT_NS 2000000000ull  // 2 s: far above any legitimate wait
+#define FA_WAIT_TIMEOUT_NS 30000000000ull  // 30 s
 #endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -57,6 +60,9 @@ __device__ __forceinline__ bool elect_one() {
 // ------------------------------------ mbarrier ----------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_inval(uint64_t* bar) {
+  asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void fence_mbar_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -101,6 +107,7 @@ __device__ __noinline__ void wait_timeout_trap(const DebugChannel dbg, uint32_t 
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, const DebugChannel dbg,
                                           uint32_t site, uint32_t tag = 0) {
   if (mbar_try_wait(bar, parity)) return;
+#if FA_WAIT_TIMEOUT_NS > 0
   const uint64_t t0 = globaltimer_ns();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
@@ -108,6 +115,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, const 
       if (globaltimer_ns() - t0 > FA_WAIT_TIMEOUT_NS) wait_timeout_trap(dbg, site, parity, tag);
     }
   }
+#else
+  while (!mbar_try_wait(bar, parity)) {
+  }
+#endif
 }
 
 // Named barrier among a subset of warps (bar.sync id, nthreads).

@@ -20,7 +20,9 @@ def _stream_ptr(stream=None):
     return ctypes.c_void_p(s.cuda_stream)
 
 
-def _dev_ptr(t, dtype, name):
+def _dev_ptr(t, dtype, name, shape=None, device=None):
+    """Device address of `t` after checking type, dtype, layout and -- when given -- the exact shape and the device
+    (an undersized or foreign buffer would be written past its end by a TMA / float4 store)."""
     if t is None:
         return None
     if not isinstance(t, torch.Tensor) or not t.is_cuda:
@@ -29,6 +31,10 @@ def _dev_ptr(t, dtype, name):
         raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
     if not t.is_contiguous():
         raise ValueError(f"{name} must be contiguous (row-major)")
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise ValueError(f"{name} must have shape {tuple(shape)}, got {tuple(t.shape)}")
+    if device is not None and t.device != device:
+        raise ValueError(f"{name} must be on {device}, got {t.device}")
     return ctypes.c_void_p(t.data_ptr())
 
 
@@ -56,8 +62,9 @@ def fa_forward(q, k, v, scale=None, out=None, stream=None):
         out = torch.empty_like(q)
     lib = load_library()
     with torch.cuda.device(q.device):
-        check(lib.fa_forward(_dev_ptr(q, torch.float16, "Q"), _dev_ptr(k, torch.float16, "K"),
-                             _dev_ptr(v, torch.float16, "V"), _dev_ptr(out, torch.float16, "O"),
+        dev, shp = q.device, (B, H, N, D)
+        check(lib.fa_forward(_dev_ptr(q, torch.float16, "Q"), _dev_ptr(k, torch.float16, "K", shp, dev),
+                             _dev_ptr(v, torch.float16, "V", shp, dev), _dev_ptr(out, torch.float16, "O", shp, dev),
                              B, H, N, D, float(scale), _stream_ptr(stream)), "fa_forward")
     return out
 
@@ -73,8 +80,9 @@ def fa_forward_f32out(q, k, v, scale=None, out=None, stream=None):
         out = torch.empty((B, H, N, D), dtype=torch.float32, device=q.device)
     lib = load_library()
     with torch.cuda.device(q.device):
-        check(lib.fa_forward_f32out(_dev_ptr(q, torch.float16, "Q"), _dev_ptr(k, torch.float16, "K"),
-                                    _dev_ptr(v, torch.float16, "V"), _dev_ptr(out, torch.float32, "O"),
+        dev, shp = q.device, (B, H, N, D)
+        check(lib.fa_forward_f32out(_dev_ptr(q, torch.float16, "Q"), _dev_ptr(k, torch.float16, "K", shp, dev),
+                                    _dev_ptr(v, torch.float16, "V", shp, dev), _dev_ptr(out, torch.float32, "O", shp, dev),
                                     B, H, N, D, float(scale), _stream_ptr(stream)), "fa_forward_f32out")
     return out
 
@@ -92,8 +100,10 @@ def fa_forward_cross(q, k, v, scale=None, out=None, stream=None):
         out = torch.empty((B, H, Nq, D), dtype=torch.float32, device=q.device)
     lib = load_library()
     with torch.cuda.device(q.device):
-        check(lib.fa_forward_cross(_dev_ptr(q, torch.float16, "Q"), _dev_ptr(k, torch.float16, "K"),
-                                   _dev_ptr(v, torch.float16, "V"), _dev_ptr(out, torch.float32, "O"),
+        dev, kshp = q.device, (B, H, Nkv, D)
+        check(lib.fa_forward_cross(_dev_ptr(q, torch.float16, "Q"), _dev_ptr(k, torch.float16, "K", kshp, dev),
+                                   _dev_ptr(v, torch.float16, "V", kshp, dev),
+                                   _dev_ptr(out, torch.float32, "O", (B, H, Nq, D), dev),
                                    B, H, Nq, Nkv, D, float(scale), _stream_ptr(stream)), "fa_forward_cross")
     return out
 
@@ -108,11 +118,14 @@ def fa_forward_partial(q, k, v, o_acc, m, l, scale, is_first, is_last, o_final=N
         o_final = torch.empty_like(q)
     lib = load_library()
     with torch.cuda.device(q.device):
-        check(lib.fa_forward_partial(_dev_ptr(q, torch.float16, "Q"), _dev_ptr(k, torch.float16, "K"),
-                                     _dev_ptr(v, torch.float16, "V"), _dev_ptr(o_acc, torch.float32, "O_acc"),
-                                     _dev_ptr(m, torch.float32, "m"), _dev_ptr(l, torch.float32, "l"),
+        dev, kshp = q.device, (B, H, Nkv, D)
+        check(lib.fa_forward_partial(_dev_ptr(q, torch.float16, "Q"), _dev_ptr(k, torch.float16, "K", kshp, dev),
+                                     _dev_ptr(v, torch.float16, "V", kshp, dev),
+                                     _dev_ptr(o_acc, torch.float32, "O_acc", (B, H, Nq, D), dev),
+                                     _dev_ptr(m, torch.float32, "m", (B, H, Nq), dev),
+                                     _dev_ptr(l, torch.float32, "l", (B, H, Nq), dev),
                                      B, H, Nq, Nkv, D, float(scale), int(bool(is_first)), int(bool(is_last)),
-                                     _dev_ptr(o_final, torch.float16, "O_final") if is_last else None,
+                                     _dev_ptr(o_final, torch.float16, "O_final", (B, H, Nq, D), dev) if is_last else None,
                                      _stream_ptr(stream)), "fa_forward_partial")
     return o_final
 
@@ -133,10 +146,11 @@ def gemm_fused_epilogue(a, b, bias=None, residual=None, out=None, stream=None):
         raise ValueError("residual must be [M, N]")
     lib = load_library()
     with torch.cuda.device(a.device):
-        check(lib.gemm_fused_epilogue(_dev_ptr(a, torch.float16, "A"), _dev_ptr(b, torch.float16, "B"),
-                                      _dev_ptr(bias, torch.float32, "bias"),
-                                      _dev_ptr(residual, torch.float32, "residual"),
-                                      _dev_ptr(out, torch.float32, "C"), M, N, K, _stream_ptr(stream)),
+        dev = a.device
+        check(lib.gemm_fused_epilogue(_dev_ptr(a, torch.float16, "A"), _dev_ptr(b, torch.float16, "B", (K, N), dev),
+                                      _dev_ptr(bias, torch.float32, "bias", (N,), dev),
+                                      _dev_ptr(residual, torch.float32, "residual", (M, N), dev),
+                                      _dev_ptr(out, torch.float32, "C", (M, N), dev), M, N, K, _stream_ptr(stream)),
               "gemm_fused_epilogue")
     return out
 
@@ -160,8 +174,9 @@ def gemm_batched(a, b, trans_b=False, alpha=1.0, out=None, stream=None):
         raise ValueError("C must be [batch, M, N]")
     lib = load_library()
     with torch.cuda.device(a.device):
-        check(lib.gemm_batched(_dev_ptr(a, torch.float16, "A"), _dev_ptr(b, torch.float16, "B"),
-                               _dev_ptr(out, torch.float32, "C"), batch, M, N, K, 1 if trans_b else 0, float(alpha),
+        check(lib.gemm_batched(_dev_ptr(a, torch.float16, "A"), _dev_ptr(b, torch.float16, "B", None, a.device),
+                               _dev_ptr(out, torch.float32, "C", (batch, M, N), a.device), batch, M, N, K,
+                               1 if trans_b else 0, float(alpha),
                                _stream_ptr(stream)), "gemm_batched")
     return out
 
@@ -176,8 +191,8 @@ def softmax_rows(x, out=None, stream=None):
         out = torch.empty_like(x)
     lib = load_library()
     with torch.cuda.device(x.device):
-        check(lib.softmax_rows(_dev_ptr(x, torch.float32, "X"), _dev_ptr(out, torch.float32, "P"), rows, N,
-                               _stream_ptr(stream)), "softmax_rows")
+        check(lib.softmax_rows(_dev_ptr(x, torch.float32, "X"), _dev_ptr(out, torch.float32, "P", (rows, N), x.device),
+                               rows, N, _stream_ptr(stream)), "softmax_rows")
     return out
 
 
@@ -191,7 +206,8 @@ def softmax_rows_f16out(x, out=None, stream=None):
         out = torch.empty((rows, N), dtype=torch.float16, device=x.device)
     lib = load_library()
     with torch.cuda.device(x.device):
-        check(lib.softmax_rows_f16out(_dev_ptr(x, torch.float32, "X"), _dev_ptr(out, torch.float16, "P"), rows, N,
+        check(lib.softmax_rows_f16out(_dev_ptr(x, torch.float32, "X"),
+                                      _dev_ptr(out, torch.float16, "P", (rows, N), x.device), rows, N,
                                       _stream_ptr(stream)), "softmax_rows_f16out")
     return out
 
@@ -223,47 +239,69 @@ def fa_forward_unfused(q, k, v, scale=None, workspace=None, stream=None):
 
 
 # ----------------------------- host-buffer variants ------------------------------------
-def _host_ptr(a, dtype, name):
+_NP_TO_TORCH = {np.dtype(np.float16): torch.float16, np.dtype(np.float32): torch.float32}
+
+
+def _host_ptr(a, dtype, name, shape=None):
+    """Host address of `a` (numpy array or torch CPU tensor) after checking dtype, layout and the exact shape: the
+    library copies extents derived from the FIRST argument's shape, so a short or mistyped buffer would be read or
+    written past its end inside cudaMemcpyAsync."""
     if a is None:
         return None
     if isinstance(a, torch.Tensor):
         if a.is_cuda:
             raise TypeError(f"{name}: the *_host entry points take host memory")
+        if a.dtype != _NP_TO_TORCH[np.dtype(dtype)]:
+            raise TypeError(f"{name} must be {_NP_TO_TORCH[np.dtype(dtype)]}, got {a.dtype}")
         if not a.is_contiguous():
             raise ValueError(f"{name} must be contiguous")
-        return ctypes.c_void_p(a.data_ptr())
-    if not isinstance(a, np.ndarray) or a.dtype != dtype or not a.flags["C_CONTIGUOUS"]:
-        raise TypeError(f"{name} must be a C-contiguous numpy array of {dtype}")
-    return ctypes.c_void_p(a.ctypes.data)
+        ptr = a.data_ptr()
+    elif isinstance(a, np.ndarray):
+        if a.dtype != np.dtype(dtype) or not a.flags["C_CONTIGUOUS"]:
+            raise TypeError(f"{name} must be a C-contiguous numpy array of {np.dtype(dtype)}")
+        ptr = a.ctypes.data
+    else:
+        raise TypeError(f"{name} must be a numpy array or a torch CPU tensor")
+    if shape is not None and tuple(a.shape) != tuple(shape):
+        raise ValueError(f"{name} must have shape {tuple(shape)}, got {tuple(a.shape)}")
+    return ctypes.c_void_p(ptr)
 
 
 def fa_forward_host(q, k, v, out, scale=None):
     """fa_forward on HOST buffers (fp16 [B,H,N,D]); copies are part of the call."""
+    if getattr(q, "ndim", 0) != 4:
+        raise ValueError("Q must be [B, H, N, D]")
     B, H, N, D = (int(x) for x in q.shape)
+    shp = (B, H, N, D)
     if scale is None:
         scale = 1.0 / float(D) ** 0.5
     lib = load_library()
-    check(lib.fa_forward_host(_host_ptr(q, np.float16, "Q"), _host_ptr(k, np.float16, "K"),
-                              _host_ptr(v, np.float16, "V"), _host_ptr(out, np.float16, "O"),
+    check(lib.fa_forward_host(_host_ptr(q, np.float16, "Q", shp), _host_ptr(k, np.float16, "K", shp),
+                              _host_ptr(v, np.float16, "V", shp), _host_ptr(out, np.float16, "O", shp),
                               B, H, N, D, float(scale)), "fa_forward_host")
     return out
 
 
 def gemm_fused_epilogue_host(a, b, bias, residual, out):
+    if getattr(a, "ndim", 0) != 2 or getattr(b, "ndim", 0) != 2 or a.shape[1] != b.shape[0]:
+        raise ValueError("A must be [M, K] and B [K, N]")
     M, K = (int(x) for x in a.shape)
     N = int(b.shape[1])
     lib = load_library()
-    check(lib.gemm_fused_epilogue_host(_host_ptr(a, np.float16, "A"), _host_ptr(b, np.float16, "B"),
-                                       _host_ptr(bias, np.float32, "bias"), _host_ptr(residual, np.float32, "residual"),
-                                       _host_ptr(out, np.float32, "C"), M, N, K), "gemm_fused_epilogue_host")
+    check(lib.gemm_fused_epilogue_host(_host_ptr(a, np.float16, "A", (M, K)), _host_ptr(b, np.float16, "B", (K, N)),
+                                       _host_ptr(bias, np.float32, "bias", (N,)),
+                                       _host_ptr(residual, np.float32, "residual", (M, N)),
+                                       _host_ptr(out, np.float32, "C", (M, N)), M, N, K), "gemm_fused_epilogue_host")
     return out
 
 
 def softmax_rows_host(x, out):
+    if getattr(x, "ndim", 0) != 2:
+        raise ValueError("X must be [rows, N]")
     rows, N = (int(v) for v in x.shape)
     lib = load_library()
-    check(lib.softmax_rows_host(_host_ptr(x, np.float32, "X"), _host_ptr(out, np.float32, "P"), rows, N),
-          "softmax_rows_host")
+    check(lib.softmax_rows_host(_host_ptr(x, np.float32, "X", (rows, N)), _host_ptr(out, np.float32, "P", (rows, N)),
+                                rows, N), "softmax_rows_host")
     return out
 
 

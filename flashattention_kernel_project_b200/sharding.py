@@ -8,8 +8,12 @@
   into the carried (O_acc, m, l) with the reference's own tile-to-tile merge rule
   (Streaming_FlashAttention_Forward_Kernel/flashattn_streaming_16x16.cu:247-261).
 
-  Two exchanges: `ring_attention` passes shards rank -> rank+1 with NCCL send/recv (the default: fastest
-  measured); `ring_attention_pull` maps every rank's K/V shard into every process (CUDA IPC over NVLink /
+  `ring_forward` is the product path: the whole loop runs inside the library (C ABI `fa_ring_forward`: the
+  partial-attention launches and grouped ncclSend / ncclRecv on a high-priority stream, tied together with events
+  from C++; every rank sends its own read-only shard straight to the rank that needs it next, so all exchanges
+  are in flight from the start and none waits for an earlier one).  The two Python-orchestrated variants below
+  are kept as the independent implementations it is tested against: `ring_attention` passes shards
+  rank -> rank+1 with NCCL send/recv; `ring_attention_pull` maps every rank's K/V shard into every process (CUDA IPC over NVLink /
   NVSwitch) and each rank fetches the shard it needs next straight from its owner with the copy engines --
   K/V are read-only, so nothing has to be passed along and the ranks do not synchronise inside the loop.
   Bit-identical results; kept as the stepping stone to reading peer K/V tiles from inside the kernel.
@@ -34,6 +38,74 @@ def shard_range(total, world_size, rank):
 def ring_schedule(world_size, rank):
     """Owner rank of the K/V shard this rank attends to at each ring step."""
     return [(rank - s) % world_size for s in range(world_size)]
+
+
+def _nccl_comm_ptr(group, device):
+    """The ncclComm_t behind `group` on `device` (created by a first collective if the group is still lazy)."""
+    pg = group if group is not None else dist.group.WORLD
+    backend = pg._get_backend(torch.device("cuda", device.index if device.index is not None else torch.cuda.current_device()))
+    ptr = backend._comm_ptr()
+    if not ptr:
+        dist.barrier(group=group, device_ids=[device.index])
+        ptr = backend._comm_ptr()
+    if not ptr:
+        raise RuntimeError("the process group has no NCCL communicator on this device")
+    return int(ptr)
+
+
+class RingWorkspace:
+    """Device memory for `ring_forward`: the carried fp32 (O_acc, m, l) and `depth` receive buffers of one K and one
+    V shard (depth = 0: world - 1 buffers, every exchange prefetched).  Reusable across calls of the same shape."""
+
+    def __init__(self, shape, world, device, depth=0):
+        from ._lib import load_library
+        B, H, n, D = (int(x) for x in shape)
+        self.shape, self.world, self.depth = (B, H, n, D), int(world), int(depth)
+        self.nbytes = int(load_library().fa_ring_workspace_bytes(B, H, n, D, self.world, self.depth))
+        if self.nbytes == 0:
+            raise ValueError("bad ring shape")
+        self.buffer = torch.empty(self.nbytes, dtype=torch.uint8, device=device)
+        if self.buffer.data_ptr() % 256:
+            raise RuntimeError("allocator returned memory that is not 256-byte aligned")
+
+
+def ring_forward(q, k, v, scale=None, group=None, out=None, workspace=None, depth=0, stream=None):
+    """Context-parallel attention over the ranks of `group` through the C ABI `fa_ring_forward` (one call per
+    rank, same shapes everywhere).  q, k, v: this rank's [B, H, N/P, D] fp16 shards; returns this rank's rows of O.
+    Nothing is synchronised on the host: the call only enqueues on `stream` and on the library's exchange stream."""
+    import ctypes
+    from ._lib import check, load_library
+    if not (q.is_cuda and k.is_cuda and v.is_cuda):
+        raise TypeError("ring_forward needs CUDA tensors (no CPU fallback exists)")
+    if q.dtype != torch.float16 or k.dtype != torch.float16 or v.dtype != torch.float16:
+        raise TypeError("Q, K, V must be float16")
+    if q.dim() != 4 or k.shape != q.shape or v.shape != q.shape:
+        raise ValueError("Q, K, V must be [B, H, N/P, D] shards of one shape")
+    if not (q.is_contiguous() and k.is_contiguous() and v.is_contiguous()):
+        raise ValueError("Q, K, V must be contiguous")
+    B, H, n, D = (int(x) for x in q.shape)
+    if scale is None:
+        scale = 1.0 / float(D) ** 0.5
+    initialised = dist.is_available() and dist.is_initialized()
+    world = dist.get_world_size(group) if initialised else 1
+    rank = dist.get_rank(group) if initialised else 0
+    if out is None:
+        out = torch.empty_like(q)
+    elif out.shape != q.shape or out.dtype != torch.float16 or out.device != q.device or not out.is_contiguous():
+        raise ValueError("out must be a contiguous float16 tensor of Q's shape on Q's device")
+    if workspace is None:
+        workspace = RingWorkspace(q.shape, world, q.device, depth)
+    elif workspace.shape != (B, H, n, D) or workspace.world != world or workspace.buffer.device != q.device:
+        raise ValueError("workspace was made for another shape, world size or device")
+    comm = _nccl_comm_ptr(group, q.device) if world > 1 else None
+    s = torch.cuda.current_stream(q.device) if stream is None else stream
+    with torch.cuda.device(q.device):
+        check(load_library().fa_ring_forward(
+            ctypes.c_void_p(q.data_ptr()), ctypes.c_void_p(k.data_ptr()), ctypes.c_void_p(v.data_ptr()),
+            ctypes.c_void_p(out.data_ptr()), B, H, n, D, float(scale), rank, world,
+            ctypes.c_void_p(comm) if comm else None, ctypes.c_void_p(workspace.buffer.data_ptr()),
+            ctypes.c_size_t(workspace.nbytes), ctypes.c_void_p(s.cuda_stream)), "fa_ring_forward")
+    return out
 
 
 def new_ring_group(ranks=None):
@@ -114,10 +186,14 @@ class PeerShards:
         self.rank = dist.get_rank(group)
         self._local = (k, v)
         handles = [None] * self.world
+        # whatever produced k and v on this rank has finished before any peer can see the handles ...
+        torch.cuda.synchronize(k.device)
         dist.all_gather_object(handles, (reduce_tensor(k), reduce_tensor(v)), group=group)
         self._shards = []
         for r, ((fk, ak), (fv, av)) in enumerate(handles):
             self._shards.append((k, v) if r == self.rank else (fk(*ak), fv(*av)))
+        # ... and no rank starts reading before every rank has mapped every shard (mirrors close())
+        dist.barrier(group=group)
 
     def owner(self, r):
         return self._shards[r]

@@ -22,6 +22,8 @@
 #ifndef FA_B200_H_
 #define FA_B200_H_
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -34,9 +36,17 @@ extern "C" {
 #define FA_ERR_NO_DEVICE (-5)      /* current device is not compute capability 10.x               */
 #define FA_ERR_DRIVER_ENTRY (-6)   /* cuTensorMapEncodeTiled could not be resolved / failed       */
 #define FA_ERR_BAD_ARGUMENT (-7)
+#define FA_ERR_NCCL (-8)           /* fa_ring_forward: an NCCL call failed (or libnccl could not be resolved: -6) */
 
 /* Library version: major*10000 + minor*100 + patch. */
 int fa_version(void);
+/*
+ * Optional one-time setup for the CURRENT device: probes it, allocates the mapped debug page and the stream-ordered
+ * memory pool of the attention kernel's tail workspace.  Every compute entry point does this lazily on first use; call
+ * fa_init() once per device beforehand when the first compute call would otherwise happen inside a CUDA stream capture
+ * (cudaHostAlloc and pool creation are not capturable).  Returns FA_OK or FA_ERR_NO_DEVICE.
+ */
+int fa_init(void);
 /* Static string for a return code of this library (negative) or of CUDA (positive). */
 const char* fa_strerror(int code);
 
@@ -86,6 +96,30 @@ int fa_forward_cross(const void* Q, const void* K, const void* V, float* O, int 
 int fa_forward_partial(const void* Q, const void* K, const void* V, float* O_acc, float* m, float* l,
                        int B, int H, int Nq, int Nkv, int D, float scale, int is_first, int is_last,
                        void* O_final, void* stream);
+
+/*
+ * Context-parallel (ring) attention over `world` ranks, one process per GPU (BASELINE config 4: B=1, H=32,
+ * N=65536, D=128 over 2/4/8 GPUs).  Rank r holds rows [r*n, (r+1)*n) of Q, K, V (fp16 [B,H,n,D]) and receives the
+ * same rows of O = softmax(scale * Q K_all^T) V_all.  The whole loop is enqueued from C++: `world` calls of the
+ * fa_forward_partial kernel on `stream`, the K/V exchange as grouped ncclSend / ncclRecv on an internal
+ * high-priority stream, tied together with events (no host synchronisation; CUDA-graph capturable).  K/V are
+ * read-only, so every rank sends its OWN shard straight to the rank that needs it next (exchange x: to rank + x,
+ * from rank - x) instead of passing shards along: the exchanges are independent, all of them are in flight from
+ * the start (as many as the workspace has receive buffers), and step 0 -- the local shard -- needs none.
+ *   nccl_comm : an ncclComm_t spanning the `world` ranks, this process being `rank` (made with
+ *               ncclCommInitRank, or borrowed from the host framework's process group); the library resolves ncclSend/ncclRecv/ncclGroupStart/End from the
+ *               libnccl.so.2 loaded in the process and links none itself.  May be NULL when world == 1.
+ *   workspace : device memory owned by the caller, 256-byte aligned, at least fa_ring_workspace_bytes(..., depth)
+ *               bytes: the carried fp32 (O_acc, m, l) + `depth` receive buffers of one K and one V shard.
+ *               depth <= 0 or >= world-1 means world-1 buffers (everything prefetched); fewer buffers are reused
+ *               in order, each exchange then waits for the step that last read its buffer.
+ * The merge of the partial results is the reference's tile-to-tile (m, l, y) rule
+ * (Streaming_FlashAttention_Forward_Kernel/flashattn_streaming_16x16.cu:247-261); the reference has no multi-GPU path.
+ * Every rank of the communicator must make the same call (same shapes) in the same order.
+ */
+size_t fa_ring_workspace_bytes(int B, int H, int n, int D, int world, int depth);
+int fa_ring_forward(const void* Q, const void* K, const void* V, void* O, int B, int H, int n, int D, float scale,
+                    int rank, int world, void* nccl_comm, void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * C = ReLU(A*B + bias[col]) + residual   (epilogue order: bias -> ReLU -> residual).
@@ -153,7 +187,9 @@ int softmax_rows_host(const float* X, float* P, int rows, int N);
 int fa_host_release(void);
 
 /*
- * Hang diagnostics: every mbarrier wait in the kernels is bounded (2 s); on expiry the kernel
+ * Hang diagnostics: every mbarrier wait in the kernels is bounded (30 s of wall clock by default, far above any
+ * legitimate wait even when the context is time-sliced or replayed under a profiler; -DFA_WAIT_TIMEOUT_NS=<ns> at
+ * build time changes the bound, 0 removes it); on expiry the kernel
  * records where it was stuck and traps.  fa_last_debug copies up to `n` 32-bit words of that
  * record (word0 = 0xDEAD0001 if a record exists; site, blockIdx.x, blockIdx.y, threadIdx.x,
  * parity, tag follow) and returns the number of words written.  The B200-native counterpart of
@@ -164,6 +200,21 @@ int fa_last_debug(unsigned int* words, int n);
 
 /* Number of kernels this library has launched in this process (all entry points). */
 unsigned long long fa_launch_count(void);
+
+/*
+ * Work decomposition of the attention kernel on a device with `sms` SMs (host arithmetic only, no device work).
+ * The reference's grid is one CTA per (query block, b*h) (FlashAttention/flashattn_forward_wmma/flashattn_forward_wmma_v4.cu:452);
+ * here an ITEM is one 256-row query block of one (b,h), CTAs of the full waves own one item each, and the items of
+ * the partial last wave are cut along K/V into equal spans of 128-key tiles, one CTA per span ("stream-K" tail; the
+ * parts of an item are merged with the (m, l, O) rule of Streaming_FlashAttention_Forward_Kernel/flashattn_streaming_16x16.cu:247-261).
+ * Writes up to max_segments rows {cta, item, kv_tile_begin, kv_tile_end, slot, tail_item} (slot -1 = whole item)
+ * into `out` (may be NULL) and returns the number of segments, or a negative FA_ERR_*.
+ * Environment FA_TAIL_SPLIT=0 (read once) disables the cut.
+ */
+int fa_plan_segments(int B, int H, int Nq, int Nkv, int sms, int* out, int max_segments);
+
+/* Tensor-map cache counters (the cache is bounded and mutex-protected); returns its capacity. */
+int fa_map_cache_stats(unsigned long long* hits, unsigned long long* misses);
 
 #ifdef __cplusplus
 }

@@ -53,3 +53,16 @@ def fa():
     if not torch.cuda.is_available():
         raise RuntimeError("GPU test selected but no CUDA device is visible")
     return pkg
+
+
+@pytest.hookimpl(hookwrapper=True)
+def pytest_runtest_makereport(item, call):
+    """A failing GPU test also reports the library's hang-diagnostic record (which bounded mbarrier wait expired)."""
+    outcome = yield
+    rep = outcome.get_result()
+    if rep.when == "call" and rep.failed and "gpu" in item.keywords:
+        try:
+            import flashattention_kernel_project_b200 as pkg
+            rep.sections.append(("fa_last_debug", repr([hex(w) for w in pkg.last_debug()])))
+        except Exception as e:  # noqa: BLE001
+            rep.sections.append(("fa_last_debug", f"unavailable: {e}"))

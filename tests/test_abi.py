@@ -115,3 +115,54 @@ def test_header_is_plain_c_and_a_c_program_links_against_the_library(tmp_path):
     assert "fa_version" in r.stdout
     if not torch.cuda.is_available():
         assert r.returncode == 2 and "-5" in r.stdout, r.stdout  # FA_ERR_NO_DEVICE, reported through fa_strerror
+
+
+def test_host_wrappers_validate_every_buffer_before_any_copy():
+    """The *_host entry points size their copies from the FIRST argument: a short, mistyped or non-contiguous K, V,
+    bias, residual or output would be read or written past its end inside cudaMemcpyAsync.  The mirror rejects
+    them on the host (numpy arrays and torch CPU tensors alike) before the library is called."""
+    import numpy as np
+    import pytest
+    import torch
+    import flashattention_kernel_project_b200 as fa
+    a, b = np.zeros((256, 64), np.float16), np.zeros((64, 128), np.float16)
+    good = np.zeros((256, 128), np.float32)
+    for bad in (np.zeros((256, 128), np.float16), np.zeros((255, 128), np.float32),
+                torch.zeros((256, 128), dtype=torch.float16), np.zeros((128, 256), np.float32).T):
+        with pytest.raises((TypeError, ValueError)):
+            fa.gemm_fused_epilogue_host(a, b, None, None, bad)
+    with pytest.raises(ValueError):
+        fa.gemm_fused_epilogue_host(a, b, np.zeros(127, np.float32), None, good)
+    with pytest.raises(ValueError):
+        fa.gemm_fused_epilogue_host(a, b, None, np.zeros((256, 64), np.float32), good)
+    q = np.zeros((1, 2, 128, 64), np.float16)
+    with pytest.raises(ValueError):
+        fa.fa_forward_host(q, q, q[:, :, :64].copy(), q.copy())
+    with pytest.raises(TypeError):
+        fa.fa_forward_host(q, q, q, np.zeros(q.shape, np.float32))
+    with pytest.raises(TypeError):
+        fa.fa_forward_host(torch.zeros(q.shape, dtype=torch.float32), q, q, q.copy())
+    x = np.zeros((8, 128), np.float32)
+    with pytest.raises(ValueError):
+        fa.softmax_rows_host(x, np.zeros((8, 64), np.float32))
+
+
+def test_ring_entry_validates_without_a_device():
+    """fa_ring_forward / fa_ring_workspace_bytes: argument checks happen before any device or NCCL work."""
+    import flashattention_kernel_project_b200 as fa
+    lib = fa.load_library()
+    full = lib.fa_ring_workspace_bytes(1, 32, 8192, 128, 8, 0)
+    state = lib.fa_ring_workspace_bytes(1, 32, 8192, 128, 1, 0)
+    shard = 32 * 8192 * 128 * 2
+    assert full == state + 7 * 2 * shard  # carried fp32 (O_acc, m, l) + world - 1 receive buffers of K and V
+    assert lib.fa_ring_workspace_bytes(1, 32, 8192, 128, 8, 2) == state + 2 * 2 * shard
+    assert lib.fa_ring_workspace_bytes(0, 32, 8192, 128, 8, 0) == 0
+    p = ctypes.c_void_p(256)
+    args = lambda **kw: [kw.get("q", p), p, p, p, 1, 2, 128, kw.get("D", 128), 0.1, kw.get("rank", 0), kw.get("world", 2),
+                         kw.get("comm", p), kw.get("ws", p), kw.get("bytes", 1 << 30), None]
+    assert lib.fa_ring_forward(*args(D=32)) == -2
+    assert lib.fa_ring_forward(*args(rank=2)) == -7
+    assert lib.fa_ring_forward(*args(q=None)) == -4
+    assert lib.fa_ring_forward(*args(comm=None)) == -4
+    assert lib.fa_ring_forward(*args(ws=ctypes.c_void_p(8))) == -3
+    assert lib.fa_ring_forward(*args(bytes=1024)) == -7  # workspace too small for the state and one receive buffer

@@ -64,8 +64,9 @@ def test_softmax_kernels_are_plain_bandwidth_kernels(sass):
 
 
 def test_kernels_keep_their_state_in_registers():
-    """cuobjdump -res-usage: no kernel uses local memory arrays; the config-3 attention kernel, the GEMM, the softmax and
-    the D = 16 kernels have no stack frame at all (the D = 64 attention instantiation keeps one 8-byte spill slot)."""
+    """cuobjdump -res-usage: no kernel uses local memory arrays; the GEMM, the softmax and the D = 16 kernels have no
+    stack frame at all; the attention kernel keeps one 4-byte spill slot in the correction warps' MERGE path (the
+    stream-K tail: once per cut item, never in a loop over keys) -- the softmax, MMA and TMA roles spill nothing."""
     import re
     import subprocess
     out = subprocess.run(["cuobjdump", "-res-usage", fa.lib_path()], capture_output=True, text=True, check=True).stdout
@@ -73,5 +74,5 @@ def test_kernels_keep_their_state_in_registers():
     assert len(entries) >= 20
     for name, reg, stack, shared, local in entries:
         assert int(local) == 0, name
-        limit = 16 if "fa_fwd_kernelILi64" in name else 0
+        limit = 8 if "fa_fwd_kernel" in name else 0
         assert int(stack) <= limit, f"{name}: stack frame of {stack} bytes"
