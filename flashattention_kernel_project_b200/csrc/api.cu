@@ -51,11 +51,13 @@ EncodeTiledFn get_encode_fn() {
 struct MapKey {
   const void* base;
   uint64_t dims[3];
+  uint64_t ld[2];
   uint32_t box[3];
   int dt, rank;
   bool operator==(const MapKey& o) const {
     return base == o.base && dt == o.dt && rank == o.rank && dims[0] == o.dims[0] && dims[1] == o.dims[1] &&
-           dims[2] == o.dims[2] && box[0] == o.box[0] && box[1] == o.box[1] && box[2] == o.box[2];
+           dims[2] == o.dims[2] && ld[0] == o.ld[0] && ld[1] == o.ld[1] && box[0] == o.box[0] && box[1] == o.box[1] &&
+           box[2] == o.box[2];
   }
 };
 constexpr int kMapCacheEntries = 64;
@@ -69,11 +71,12 @@ MapCache g_map_cache;
 std::atomic<unsigned long long> g_map_hits{0}, g_map_misses{0};
 
 int encode_map(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, const void* base, int rank,
-               const uint64_t* dims, const uint32_t* box);
+               const uint64_t* dims, const uint32_t* box, const uint64_t* ld);
 
-// rank-2/3 tiled map over a row-major tensor whose innermost extent is dims[0]; 128B swizzle.
+// rank-2/3 tiled map over a row-major tensor whose innermost extent is dims[0]; 128B swizzle.  ld (may be null =
+// densely packed): element pitch of dimension 1 (the row pitch) and of dimension 2 (the batch stride).
 int make_map(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, const void* base, int rank,
-             const uint64_t* dims, const uint32_t* box) {
+             const uint64_t* dims, const uint32_t* box, const uint64_t* ld = nullptr) {
   MapKey key{};
   key.base = base;
   key.dt = static_cast<int>(dt);
@@ -82,6 +85,8 @@ int make_map(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, const voi
     key.dims[i] = dims[i];
     key.box[i] = box[i];
   }
+  key.ld[0] = ld != nullptr ? ld[0] : 0;
+  key.ld[1] = ld != nullptr ? ld[1] : 0;
   {
     std::lock_guard<std::mutex> lock(g_map_cache.mu);
     for (int i = 0; i < g_map_cache.used; ++i)
@@ -91,7 +96,7 @@ int make_map(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, const voi
         return FA_OK;
       }
   }
-  const int rc = encode_map(map, dt, elem_bytes, base, rank, dims, box);
+  const int rc = encode_map(map, dt, elem_bytes, base, rank, dims, box, ld);
   if (rc != FA_OK) return rc;
   g_map_misses.fetch_add(1, std::memory_order_relaxed);
   std::lock_guard<std::mutex> lock(g_map_cache.mu);
@@ -102,7 +107,7 @@ int make_map(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, const voi
 }
 
 int encode_map(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, const void* base, int rank,
-               const uint64_t* dims, const uint32_t* box) {
+               const uint64_t* dims, const uint32_t* box, const uint64_t* ld) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) return FA_ERR_DRIVER_ENTRY;
   cuuint64_t gdim[3];
@@ -114,7 +119,7 @@ int encode_map(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, const v
     gdim[i] = dims[i];
     bdim[i] = box[i];
     pitch *= dims[i];
-    if (i < rank - 1) gstride[i] = pitch;
+    if (i < rank - 1) gstride[i] = (ld != nullptr && ld[i] != 0) ? ld[i] * static_cast<uint64_t>(elem_bytes) : pitch;
   }
   const CUresult r = fn(map, dt, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim, gstride, bdim, estride,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -381,8 +386,12 @@ struct GemmCall {
   const float* residual;
   float* C;
   int batch, M, N, K;
-  bool trans_b, relu;
+  bool trans_b;
+  int act;
   float alpha;
+  // element pitches; 0 = densely packed.  lda/ldb/ldc: row pitch of A, B (its stored rows: K-rows of [K,N], N-rows of
+  // [N,K]) and C / residual; sa/sb/sc: distance between consecutive batch entries.
+  long long lda = 0, ldb = 0, ldc = 0, sa = 0, sb = 0, sc = 0;
 };
 
 int run_gemm(const GemmCall& c, void* stream) {
@@ -392,6 +401,15 @@ int run_gemm(const GemmCall& c, void* stream) {
   if ((N & 7) != 0 || (K & 7) != 0) return FA_ERR_MISALIGNED;
   if (!aligned16(c.A) || !aligned16(c.Bm) || !aligned16(c.C) || !aligned16(c.bias) || !aligned16(c.residual))
     return FA_ERR_MISALIGNED;
+  if (c.act < GEMM_ACT_IDENTITY || c.act > GEMM_ACT_SILU) return FA_ERR_BAD_ARGUMENT;
+  // leading dimensions: at least the row they hold, 16-byte multiples (TMA global strides)
+  const long long b_row = c.trans_b ? K : N, b_rows = c.trans_b ? N : K;
+  if (c.lda < 0 || c.ldb < 0 || c.ldc < 0 || c.sa < 0 || c.sb < 0 || c.sc < 0) return FA_ERR_BAD_ARGUMENT;
+  if ((c.lda != 0 && c.lda < K) || (c.ldb != 0 && c.ldb < b_row) || (c.ldc != 0 && c.ldc < N)) return FA_ERR_BAD_ARGUMENT;
+  if ((c.lda & 7) || (c.ldb & 7) || (c.ldc & 3) || (c.sa & 7) || (c.sb & 7) || (c.sc & 3)) return FA_ERR_MISALIGNED;
+  const uint64_t lda = c.lda ? c.lda : K, ldb = c.ldb ? c.ldb : b_row, ldc = c.ldc ? c.ldc : N;
+  const uint64_t sa = c.sa ? c.sa : lda * M, sb = c.sb ? c.sb : ldb * b_rows, sc = c.sc ? c.sc : ldc * M;
+  const uint64_t ld_a[2] = {lda, sa}, ld_b[2] = {ldb, sb}, ld_c[2] = {ldc, sc};
   DeviceState* st = nullptr;
   int rc = current_device_state(&st);
   if (rc != FA_OK) return rc;
@@ -399,21 +417,21 @@ int run_gemm(const GemmCall& c, void* stream) {
   CUtensorMap ma, mb, mr, mc;
   const uint64_t da[3] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M), Z};
   const uint32_t ba[3] = {64, 128, 1};
-  if ((rc = make_map(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, c.A, 3, da, ba)) != FA_OK) return rc;
+  if ((rc = make_map(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, c.A, 3, da, ba, ld_a)) != FA_OK) return rc;
   if (c.trans_b) {  // [N,K] rows: the same K-major boxes as A
     const uint64_t db[3] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N), Z};
-    if ((rc = make_map(&mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, c.Bm, 3, db, ba)) != FA_OK) return rc;
+    if ((rc = make_map(&mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, c.Bm, 3, db, ba, ld_b)) != FA_OK) return rc;
   } else {
     const uint64_t db[3] = {static_cast<uint64_t>(N), static_cast<uint64_t>(K), Z};
     const uint32_t bb[3] = {64, 64, 1};
-    if ((rc = make_map(&mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, c.Bm, 3, db, bb)) != FA_OK) return rc;
+    if ((rc = make_map(&mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, c.Bm, 3, db, bb, ld_b)) != FA_OK) return rc;
   }
   // epilogue blocks: 128 rows x 32 fp32 columns of C / residual
   const uint64_t dc[3] = {static_cast<uint64_t>(N), static_cast<uint64_t>(M), Z};
   const uint32_t bc[3] = {GemmCfg::kEpiCols, GemmCfg::kBM, 1};
-  if ((rc = make_map(&mc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, c.C, 3, dc, bc)) != FA_OK) return rc;
-  if (c.residual != nullptr) {
-    if ((rc = make_map(&mr, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, c.residual, 3, dc, bc)) != FA_OK) return rc;
+  if ((rc = make_map(&mc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, c.C, 3, dc, bc, ld_c)) != FA_OK) return rc;
+  if (c.residual != nullptr) {  // the residual shares C's layout
+    if ((rc = make_map(&mr, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, c.residual, 3, dc, bc, ld_c)) != FA_OK) return rc;
   } else {
     mr = mc;  // never dereferenced without a residual
   }
@@ -430,7 +448,7 @@ int run_gemm(const GemmCall& c, void* stream) {
   p.m_blocks = (M + 255) / 256;  // 256 x 256 output tiles, one per CTA pair
   p.n_blocks = (N + GemmCfg::kBN - 1) / GemmCfg::kBN;
   p.alpha = c.alpha;
-  p.relu = c.relu ? 1 : 0;
+  p.act = c.act;
   p.bias = c.bias;
   p.residual = c.residual;
   p.C = c.C;
@@ -451,7 +469,7 @@ int run_gemm(const GemmCall& c, void* stream) {
 
 int run_gemm(const void* A, const void* Bm, const float* bias, const float* residual, float* C, int M, int N, int K,
              void* stream) {
-  const GemmCall c{A, Bm, bias, residual, C, 1, M, N, K, false, true, 1.0f};
+  const GemmCall c{A, Bm, bias, residual, C, 1, M, N, K, false, GEMM_ACT_RELU, 1.0f};
   return run_gemm(c, stream);
 }
 
@@ -800,7 +818,22 @@ int gemm_fused_epilogue(const void* A, const void* Bm, const float* bias, const 
 
 int gemm_batched(const void* A, const void* Bm, float* C, int batch, int M, int N, int K, int trans_b, float alpha,
                  void* stream) {
-  const GemmCall c{A, Bm, nullptr, nullptr, C, batch, M, N, K, trans_b != 0, false, alpha};
+  const GemmCall c{A, Bm, nullptr, nullptr, C, batch, M, N, K, trans_b != 0, GEMM_ACT_IDENTITY, alpha};
+  return run_gemm(c, stream);
+}
+
+int gemm_fused_epilogue_act(const void* A, const void* Bm, const float* bias, const float* residual, float* C, int M,
+                            int N, int K, int act, void* stream) {
+  const GemmCall c{A, Bm, bias, residual, C, 1, M, N, K, false, act, 1.0f};
+  return run_gemm(c, stream);
+}
+
+int gemm_batched_strided(const void* A, const void* Bm, float* C, int batch, int M, int N, int K, long long lda,
+                         long long ldb, long long ldc, long long stride_a, long long stride_b, long long stride_c,
+                         int trans_b, float alpha, void* stream) {
+  GemmCall c{A, Bm, nullptr, nullptr, C, batch, M, N, K, trans_b != 0, GEMM_ACT_IDENTITY, alpha};
+  c.lda = lda; c.ldb = ldb; c.ldc = ldc;
+  c.sa = stride_a; c.sb = stride_b; c.sc = stride_c;
   return run_gemm(c, stream);
 }
 
@@ -818,13 +851,13 @@ int fa_forward_unfused(const void* Q, const void* K, const void* V, float* O, fl
   const long long bh = static_cast<long long>(B) * H;
   if (bh > 0x7fffffffll || bh * N > 0x7fffffffll) return FA_ERR_BAD_SHAPE;
   // stage A: S = scale * Q K^T  (K as [N, D] rows = the transposed-B form)
-  const GemmCall qk{Q, K, nullptr, nullptr, S, static_cast<int>(bh), N, N, D, true, false, scale};
+  const GemmCall qk{Q, K, nullptr, nullptr, S, static_cast<int>(bh), N, N, D, true, GEMM_ACT_IDENTITY, scale};
   int rc = run_gemm(qk, stream);
   if (rc != FA_OK) return rc;
   // stage B: P = softmax_rows(S), rounded to fp16 for the tensor core
   if ((rc = run_softmax(S, static_cast<__half*>(P), static_cast<int>(bh * N), N, stream)) != FA_OK) return rc;
   // stage C: O = P V
-  const GemmCall pv{P, V, nullptr, nullptr, O, static_cast<int>(bh), N, D, N, false, false, 1.0f};
+  const GemmCall pv{P, V, nullptr, nullptr, O, static_cast<int>(bh), N, D, N, false, GEMM_ACT_IDENTITY, 1.0f};
   return run_gemm(pv, stream);
 }
 

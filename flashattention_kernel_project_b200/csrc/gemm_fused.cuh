@@ -34,12 +34,19 @@ struct GemmParams {
   int M, N, K, batch;
   int m_blocks, n_blocks;  // ceil(M/256), ceil(N/256): tiles of the CTA pair, per batch entry
   float alpha;             // C = act(alpha * A*op(B) + bias) + residual
-  int relu;                // 1: ReLU between bias and residual (the fused-epilogue contract), 0: identity
+  int act;                 // GemmAct applied between bias and residual (1 = ReLU: the reference's fused-epilogue contract)
   const float* bias;       // [N] or null
   const float* residual;   // [M,N] or null
   float* C;                // [M,N]
   DebugChannel dbg;
 };
+
+// Epilogue activations: the reference has ReLU only (tensorcore_gemm_fused_epilogue.cu:117, gemm_fused_epilogue.cu:35-37);
+// GELU (exact, erf form) and SiLU complete the surface.  Values match FA_ACT_* in fa_b200.h.
+enum GemmAct : int { GEMM_ACT_IDENTITY = 0, GEMM_ACT_RELU = 1, GEMM_ACT_GELU = 2, GEMM_ACT_SILU = 3 };
+
+__device__ __forceinline__ float gemm_act_gelu(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gemm_act_silu(float x) { return x / (1.f + expf(-x)); }
 
 struct GemmCfg {
   static constexpr int kBM = 128;   // rows per CTA (256 per pair)
@@ -303,8 +310,12 @@ gemm_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
             v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
           }
-          if (p.relu) {
+          if (p.act == GEMM_ACT_RELU) {
             v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+          } else if (p.act == GEMM_ACT_GELU) {
+            v.x = gemm_act_gelu(v.x); v.y = gemm_act_gelu(v.y); v.z = gemm_act_gelu(v.z); v.w = gemm_act_gelu(v.w);
+          } else if (p.act == GEMM_ACT_SILU) {
+            v.x = gemm_act_silu(v.x); v.y = gemm_act_silu(v.y); v.z = gemm_act_silu(v.z); v.w = gemm_act_silu(v.w);
           }
           float4* const slot = reinterpret_cast<float4*>(rowp + ((q ^ (row_in_tile & 7)) << 4));
           if (has_res) {

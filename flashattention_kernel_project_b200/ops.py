@@ -130,8 +130,15 @@ def fa_forward_partial(q, k, v, o_acc, m, l, scale, is_first, is_last, o_final=N
     return o_final
 
 
-def gemm_fused_epilogue(a, b, bias=None, residual=None, out=None, stream=None):
-    """C = ReLU(A @ B + bias) + residual; A fp16 [M,K], B fp16 [K,N], fp32 bias/residual/C."""
+ACTIVATIONS = {"identity": 0, "relu": 1, "gelu": 2, "silu": 3}  # FA_ACT_* of include/fa_b200.h
+
+
+def gemm_fused_epilogue(a, b, bias=None, residual=None, out=None, stream=None, act="relu"):
+    """C = act(A @ B + bias) + residual; A fp16 [M,K], B fp16 [K,N], fp32 bias/residual/C.
+    act = "relu" is the reference's contract (tensorcore_gemm_fused_epilogue.cu:109-126); "identity", "gelu" (exact,
+    erf form) and "silu" go through gemm_fused_epilogue_act."""
+    if act not in ACTIVATIONS:
+        raise ValueError(f"act must be one of {sorted(ACTIVATIONS)}")
     _require_cuda(a, "A")
     _require_cuda(b, "B")
     if a.dim() != 2 or b.dim() != 2 or a.shape[1] != b.shape[0]:
@@ -147,16 +154,40 @@ def gemm_fused_epilogue(a, b, bias=None, residual=None, out=None, stream=None):
     lib = load_library()
     with torch.cuda.device(a.device):
         dev = a.device
-        check(lib.gemm_fused_epilogue(_dev_ptr(a, torch.float16, "A"), _dev_ptr(b, torch.float16, "B", (K, N), dev),
-                                      _dev_ptr(bias, torch.float32, "bias", (N,), dev),
-                                      _dev_ptr(residual, torch.float32, "residual", (M, N), dev),
-                                      _dev_ptr(out, torch.float32, "C", (M, N), dev), M, N, K, _stream_ptr(stream)),
-              "gemm_fused_epilogue")
+        ptrs = (_dev_ptr(a, torch.float16, "A"), _dev_ptr(b, torch.float16, "B", (K, N), dev),
+                _dev_ptr(bias, torch.float32, "bias", (N,), dev),
+                _dev_ptr(residual, torch.float32, "residual", (M, N), dev),
+                _dev_ptr(out, torch.float32, "C", (M, N), dev))
+        if act == "relu":
+            check(lib.gemm_fused_epilogue(*ptrs, M, N, K, _stream_ptr(stream)), "gemm_fused_epilogue")
+        else:
+            check(lib.gemm_fused_epilogue_act(*ptrs, M, N, K, ACTIVATIONS[act], _stream_ptr(stream)),
+                  "gemm_fused_epilogue_act")
     return out
+
+
+def _strided3(t, dtype, name, device=None):
+    """(pointer, row pitch, batch stride) of a [batch, rows, cols] tensor whose last dimension is contiguous: a dense
+    tensor or a view of one (a head of a [B,N,H,D] tensor, a sub-matrix, a padded leading dimension)."""
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError(f"{name} must be a CUDA tensor (no CPU fallback exists)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    if device is not None and t.device != device:
+        raise ValueError(f"{name} must be on {device}, got {t.device}")
+    if t.dim() != 3 or (t.shape[2] > 1 and t.stride(2) != 1):
+        raise ValueError(f"{name} must be [batch, rows, cols] with a contiguous last dimension")
+    ld = int(t.stride(1)) if t.shape[1] > 1 else int(t.shape[2])
+    sb = int(t.stride(0)) if t.shape[0] > 1 else ld * int(t.shape[1])
+    if ld < t.shape[2] or sb <= 0:
+        raise ValueError(f"{name}: overlapping or broadcast strides are not supported")
+    return ctypes.c_void_p(t.data_ptr()), ld, sb
 
 
 def gemm_batched(a, b, trans_b=False, alpha=1.0, out=None, stream=None):
     """C[z] = alpha * A[z] @ op(B[z]); A fp16 [batch,M,K]; B fp16 [batch,K,N], or [batch,N,K] with trans_b; C fp32.
+    Dense tensors go through gemm_batched, views with a contiguous last dimension (row pitch / batch stride different
+    from the packed ones) through gemm_batched_strided -- same kernel, the pitches go into the TMA descriptors.
 
     trans_b=False, alpha=1: wmma_batched_gemm_kernel (gemm_4_9_tensorcore_batched.cu:42-46);
     trans_b=True, alpha=scale: QK_wmma_kernel (qk_wmma_5_1_2.cu:32-38)."""
@@ -174,10 +205,16 @@ def gemm_batched(a, b, trans_b=False, alpha=1.0, out=None, stream=None):
         raise ValueError("C must be [batch, M, N]")
     lib = load_library()
     with torch.cuda.device(a.device):
-        check(lib.gemm_batched(_dev_ptr(a, torch.float16, "A"), _dev_ptr(b, torch.float16, "B", None, a.device),
-                               _dev_ptr(out, torch.float32, "C", (batch, M, N), a.device), batch, M, N, K,
-                               1 if trans_b else 0, float(alpha),
-                               _stream_ptr(stream)), "gemm_batched")
+        if a.is_contiguous() and b.is_contiguous() and out.is_contiguous():
+            check(lib.gemm_batched(_dev_ptr(a, torch.float16, "A"), _dev_ptr(b, torch.float16, "B", None, a.device),
+                                   _dev_ptr(out, torch.float32, "C", (batch, M, N), a.device), batch, M, N, K,
+                                   1 if trans_b else 0, float(alpha), _stream_ptr(stream)), "gemm_batched")
+        else:
+            pa, lda, sa = _strided3(a, torch.float16, "A")
+            pb, ldb, sb = _strided3(b, torch.float16, "B", a.device)
+            pc, ldc, sc = _strided3(out, torch.float32, "C", a.device)
+            check(lib.gemm_batched_strided(pa, pb, pc, batch, M, N, K, lda, ldb, ldc, sa, sb, sc, 1 if trans_b else 0,
+                                           float(alpha), _stream_ptr(stream)), "gemm_batched_strided")
     return out
 
 

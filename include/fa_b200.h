@@ -132,6 +132,18 @@ int gemm_fused_epilogue(const void* A, const void* Bm, const float* bias, const 
                         int M, int N, int K, void* stream);
 
 /*
+ * The same kernel with a selectable activation between bias and residual: C = act(A*B + bias[col]) + residual.
+ * FA_ACT_RELU is gemm_fused_epilogue; identity / exact (erf) GELU / SiLU complete the epilogue surface -- the
+ * reference implements ReLU only (tensorcore_gemm_fused_epilogue.cu:117; gemm_fused_epilogue.cu:35-37).
+ */
+#define FA_ACT_IDENTITY 0
+#define FA_ACT_RELU 1
+#define FA_ACT_GELU 2 /* 0.5 x (1 + erf(x / sqrt 2)) */
+#define FA_ACT_SILU 3 /* x / (1 + exp(-x)) */
+int gemm_fused_epilogue_act(const void* A, const void* Bm, const float* bias, const float* residual, float* C,
+                            int M, int N, int K, int act, void* stream);
+
+/*
  * Batched plain GEMM with a scale: C[z] = alpha * A[z] * op(B[z]) for z in [0, batch), no bias / activation.
  *   A fp16 [batch,M,K]; Bm fp16 [batch,K,N] if trans_b == 0, fp16 [batch,N,K] if trans_b != 0 (C = alpha*A*B^T);
  *   C fp32 [batch,M,N]; all row-major and densely packed; K % 8 == 0 and N % 8 == 0.
@@ -144,6 +156,19 @@ int gemm_fused_epilogue(const void* A, const void* Bm, const float* bias, const 
  */
 int gemm_batched(const void* A, const void* Bm, float* C, int batch, int M, int N, int K, int trans_b, float alpha,
                  void* stream);
+
+/*
+ * gemm_batched on strided operands (BLAS-style leading dimensions and batch strides, all in ELEMENTS; 0 = densely
+ * packed): row pitches lda (A rows of K), ldb (B rows: N if trans_b == 0, K otherwise), ldc (C rows of N) and the
+ * distances stride_a / stride_b / stride_c between consecutive batch entries.  Pitches and strides must keep rows
+ * 16-byte aligned (multiples of 8 fp16 / 4 fp32 elements).  The reference hard-codes the packed case
+ * (strideA = M*K, strideB = K*N, strideC = M*N, leading dimensions K, N, N:
+ * GEMM/gemm_tensorcore_batched/gemm_4_9_tensorcore_batched.cu:58-60,77-78,85); with strides the same kernel runs
+ * on sub-matrices and interleaved batches, e.g. one head of a [B,N,H,D] tensor, without a copy.
+ */
+int gemm_batched_strided(const void* A, const void* Bm, float* C, int batch, int M, int N, int K, long long lda,
+                         long long ldb, long long ldc, long long stride_a, long long stride_b, long long stride_c,
+                         int trans_b, float alpha, void* stream);
 
 /*
  * Row softmax, P[r, :] = softmax(X[r, :]) with max subtraction; X, P fp32 [rows, N]; in place allowed.

@@ -296,10 +296,23 @@ void fa_oracle_gemm_fused(const float* A, const float* B, const float* bias, con
   }
 }
 
+/* Activation between bias and residual.  1 = the reference's ReLU (`val > 0.0f ? val : 0.0f`,
+ * tensorcore_gemm_fused_epilogue.cu:150).  0 / 2 / 3 (identity, exact GELU, SiLU) are this engine's extension of
+ * the epilogue surface: the reference has no such code, so they are PARITY-UNPINNED and
+ * checked against their defining formulas in float64 (tests/test_oracle.py). */
+static float oracle_act(float val, int act) {
+  switch (act) {
+    case 1: return val > 0.0f ? val : 0.0f;
+    case 2: return 0.5f * val * (1.0f + erff(val * 0.70710678118654752f));
+    case 3: return val / (1.0f + expf(-val));
+    default: return val;
+  }
+}
+
 /* The same contraction on fp16 operands widened to fp32 (what the GPU kernel is fed, :192-195);
  * rows [row_begin,row_end) of A only; out is [row_end-row_begin, N]. */
-void fa_oracle_gemm_fused_f16(const uint16_t* A, const uint16_t* B, const float* bias, const float* residual,
-                              float* out, int M, int N, int K, int row_begin, int row_end, int nthreads) {
+void fa_oracle_gemm_fused_f16_act(const uint16_t* A, const uint16_t* B, const float* bias, const float* residual,
+                                  float* out, int M, int N, int K, int row_begin, int row_end, int act, int nthreads) {
   (void)M;
 #ifdef _OPENMP
   if (nthreads > 0) omp_set_num_threads(nthreads);
@@ -325,7 +338,7 @@ void fa_oracle_gemm_fused_f16(const uint16_t* A, const uint16_t* B, const float*
       float* o = out + (size_t)(i - row_begin) * N;
       for (int j = 0; j < N; ++j) {
         float val = acc[j] + (bias ? bias[j] : 0.0f);
-        val = val > 0.0f ? val : 0.0f;
+        val = oracle_act(val, act);
         val += residual ? residual[(size_t)i * N + j] : 0.0f;
         o[j] = val;
       }
@@ -334,6 +347,10 @@ void fa_oracle_gemm_fused_f16(const uint16_t* A, const uint16_t* B, const float*
     free(acc);
   }
   free(Bf);
+}
+void fa_oracle_gemm_fused_f16(const uint16_t* A, const uint16_t* B, const float* bias, const float* residual,
+                              float* out, int M, int N, int K, int row_begin, int row_end, int nthreads) {
+  fa_oracle_gemm_fused_f16_act(A, B, bias, residual, out, M, N, K, row_begin, row_end, 1, nthreads);
 }
 
 /* ---------------------------------------------------------------------------------------

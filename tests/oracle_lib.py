@@ -45,6 +45,7 @@ class Oracle:
         L.fa_oracle_softmax_rows.argtypes = [_f32p, _f32p, c_ll, c_int, c_int]
         L.fa_oracle_gemm_fused.argtypes = [_f32p, _f32p, ctypes.c_void_p, ctypes.c_void_p, _f32p] + [c_int] * 6
         L.fa_oracle_gemm_fused_f16.argtypes = [_u16p, _u16p, ctypes.c_void_p, ctypes.c_void_p, _f32p] + [c_int] * 6
+        L.fa_oracle_gemm_fused_f16_act.argtypes = [_u16p, _u16p, ctypes.c_void_p, ctypes.c_void_p, _f32p] + [c_int] * 7
         L.fa_oracle_gemm_batched.argtypes = [_f32p, _f32p, _f32p] + [c_int] * 5
         L.fa_oracle_qk_scores.argtypes = [_f32p, _f32p, _f32p] + [c_int] * 4 + [c_float, c_int]
         L.fa_oracle_streaming_ref_f16.argtypes = [_u16p, _u16p, _u16p, _f32p] + [c_int] * 5 + [c_float]
@@ -109,14 +110,16 @@ class Oracle:
         self.L.fa_oracle_gemm_fused(a, b, _opt_f32(bias), _opt_f32(residual), out, M, N, K, row_begin, row_end, nthreads)
         return out
 
-    def gemm_fused_f16(self, a, b, bias, residual, row_begin=0, row_end=None, nthreads=0):
-        """fp16 operands (widened to fp32, as the GPU is fed); returns rows [row_begin, row_end)."""
+    def gemm_fused_f16(self, a, b, bias, residual, row_begin=0, row_end=None, nthreads=0, act="relu"):
+        """fp16 operands (widened to fp32, as the GPU is fed); returns rows [row_begin, row_end).
+        act: "relu" (the reference's epilogue) | "identity" | "gelu" | "silu" (extensions, parity-unpinned)."""
         M, K = a.shape
         N = b.shape[1]
         row_end = M if row_end is None else row_end
         out = np.empty((row_end - row_begin, N), dtype=np.float32)
-        self.L.fa_oracle_gemm_fused_f16(_as_u16(a), _as_u16(b), _opt_f32(bias), _opt_f32(residual), out, M, N, K,
-                                        row_begin, row_end, nthreads)
+        self.L.fa_oracle_gemm_fused_f16_act(_as_u16(a), _as_u16(b), _opt_f32(bias), _opt_f32(residual), out, M, N, K,
+                                            row_begin, row_end, {"identity": 0, "relu": 1, "gelu": 2, "silu": 3}[act],
+                                            nthreads)
         return out
 
     def gemm_batched(self, a, b, nthreads=0):

@@ -151,3 +151,50 @@ def test_many_tiny_batch_entries(fa, oracle):
     assert oracle.max_abs(got, ref) <= TOL_ABS and oracle.rel_l2(got, ref) <= TOL_REL
     sel = [0, 73, 74, 2047, 4095]
     assert oracle.max_abs(got[sel], oracle.gemm_batched(a[sel].astype(np.float32), b[sel].astype(np.float32))) <= TOL_ABS
+
+
+def test_strided_operands_need_no_copy(fa, oracle):
+    """gemm_batched_strided: leading dimensions and batch strides go into the TMA descriptors.  Views of larger
+    tensors -- one head of a [B, N, H, D] activation, a padded leading dimension, a column block of C -- give the
+    same numbers as their packed copies, bit for bit (the kernel sees the same tiles in the same order).  The
+    reference hard-codes the packed strides (gemm_4_9_tensorcore_batched.cu:58-60)."""
+    g = torch.Generator(device="cuda").manual_seed(3)
+    B, N, H, D = 3, 200, 4, 64
+    x = (torch.rand((B, N, H, D), device="cuda", generator=g) * 2 - 1).half()
+    y = (torch.rand((B, N, H, D), device="cuda", generator=g) * 2 - 1).half()
+    for h in range(H):
+        q, k = x[:, :, h, :], y[:, :, h, :]  # [B, N, D] views: row pitch H*D, batch stride N*H*D
+        assert not q.is_contiguous()
+        got = fa.gemm_batched(q, k, trans_b=True, alpha=0.125)
+        want = fa.gemm_batched(q.contiguous(), k.contiguous(), trans_b=True, alpha=0.125)
+        assert torch.equal(got, want)
+    ref = oracle.qk_scores(x[:, :, 1, :].float().cpu().numpy(), y[:, :, 1, :].float().cpu().numpy(), 0.125)
+    got = fa.gemm_batched(x[:, :, 1, :], y[:, :, 1, :], trans_b=True, alpha=0.125).cpu().numpy()
+    assert oracle.max_abs(got, ref) <= TOL_ABS and oracle.rel_l2(got, ref) <= TOL_REL
+    # padded leading dimensions of A, B ([K, N] form) and C; C written into a column block of a wider buffer
+    batch, M, Nn, K = 2, 136, 72, 40
+    a_big = (torch.rand((batch, M, K + 24), device="cuda", generator=g) * 2 - 1).half()
+    b_big = (torch.rand((batch, K + 8, Nn + 16), device="cuda", generator=g) * 2 - 1).half()
+    c_big = torch.full((batch, M, Nn + 56), -7.0, device="cuda")
+    a, b, c = a_big[:, :, :K], b_big[:, 8:, 8:8 + Nn], c_big[:, :, 32:32 + Nn]
+    fa.gemm_batched(a, b, out=c)
+    want = fa.gemm_batched(a.contiguous(), b.contiguous())
+    torch.cuda.synchronize()
+    assert torch.equal(c, want)
+    assert (c_big[:, :, :32] == -7.0).all() and (c_big[:, :, 32 + Nn:] == -7.0).all()  # nothing written outside the block
+
+
+def test_strided_entry_validates_pitches(fa):
+    import ctypes
+    lib = fa.load_library()
+    a = torch.zeros((2, 64, 64), device="cuda", dtype=torch.float16)
+    c = torch.zeros((2, 64, 64), device="cuda")
+    p = lambda x: ctypes.c_void_p(x.data_ptr())
+    call = lambda lda=0, ldb=0, ldc=0, sa=0, sb=0, sc=0: lib.gemm_batched_strided(
+        p(a), p(a), p(c), 2, 64, 64, 64, lda, ldb, ldc, sa, sb, sc, 0, 1.0, None)
+    assert call() == 0
+    assert call(lda=32) == -7      # a leading dimension shorter than the row
+    assert call(ldc=66) == -3      # fp32 rows must stay 16-byte aligned
+    assert call(lda=68) == -3      # fp16 rows must stay 16-byte aligned
+    assert call(sa=-64) == -7
+    torch.cuda.synchronize()

@@ -180,3 +180,33 @@ def test_gemm_residual_in_place(fa, oracle):
     assert oracle.max_abs(got, ref) <= 2e-3 and oracle.rel_l2(got, ref) <= 1e-3
     separate = _gemm(fa, a, b, bias, res)
     assert np.array_equal(got, separate)
+
+
+@pytest.mark.parametrize("act", ["identity", "relu", "gelu", "silu"])
+@pytest.mark.parametrize("shape", [(129, 264, 72), (512, 512, 256)])
+def test_gemm_epilogue_activations(fa, oracle, act, shape):
+    """gemm_fused_epilogue_act: act between bias and residual.  "relu" is the reference's epilogue
+    (tensorcore_gemm_fused_epilogue.cu:109-126) and must equal gemm_fused_epilogue bit for bit; identity / GELU /
+    SiLU are checked against the oracle's restatement of the same order of operations."""
+    M, N, K = shape
+    a, b, bias, res = _gemm_inputs(M, N, K, seed=7 + M)
+    ta, tb, tbias, tres = (torch.from_numpy(x).cuda() for x in (a, b, bias, res))
+    got = fa.gemm_fused_epilogue(ta, tb, tbias, tres, act=act)
+    torch.cuda.synchronize()
+    ref = oracle.gemm_fused_f16(a, b, bias, res, act=act)
+    assert oracle.max_abs(got.cpu().numpy(), ref) <= 2e-3 and oracle.rel_l2(got.cpu().numpy(), ref) <= 1e-3
+    if act == "relu":
+        assert torch.equal(got, fa.gemm_fused_epilogue(ta, tb, tbias, tres))
+    # without bias and residual the activation is applied to the bare product
+    got2 = fa.gemm_fused_epilogue(ta, tb, None, None, act=act).cpu().numpy()
+    ref2 = oracle.gemm_fused_f16(a, b, None, None, act=act)
+    assert oracle.max_abs(got2, ref2) <= 2e-3 and oracle.rel_l2(got2, ref2) <= 1e-3
+
+
+def test_gemm_rejects_unknown_activation(fa):
+    import ctypes
+    lib = fa.load_library()
+    t = torch.zeros((128, 128), device="cuda", dtype=torch.float16)
+    c = torch.zeros((128, 128), device="cuda")
+    p = lambda x: ctypes.c_void_p(x.data_ptr())
+    assert lib.gemm_fused_epilogue_act(p(t), p(t), None, None, p(c), 128, 128, 128, 9, None) == -7

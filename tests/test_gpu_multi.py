@@ -1,6 +1,8 @@
 """Multi-GPU GPU tests (skipped on a single-GPU box; run with `gpurun --gpus 2`): (b,h) sharding with no
-collective, and the ring / context-parallel path with fa_forward_partial -- K/V passed along with NCCL send/recv, and
-pulled from their owners through CUDA IPC peer mappings."""
+collective, and the ring / context-parallel path -- the product entry fa_ring_forward (C++ loop, NCCL exchange), and
+the two Python-orchestrated rings it is checked against: K/V passed along with NCCL send/recv, and pulled from their
+owners through CUDA IPC peer mappings.  The driver's 1-GPU box skips these; the ring's parity at 2 / 4 / 8 GPUs is
+also checked inside `bench.py --gpus N` (extras.ring_cfg4.parity), which the driver does run."""
 import os
 import socket
 
@@ -42,6 +44,18 @@ def _worker(rank, world, port, mode, q, k, v, scale, out_path):
             qs, ks, vs = (x[:, :, sl].contiguous().cuda() for x in (q, k, v))
             out = fa.ring_attention(qs, ks, vs, scale, group=fa.new_ring_group())
             torch.cuda.synchronize()
+            if mode == "native":
+                # the product path: the whole loop inside the library (fa_ring_forward: partial-attention launches +
+                # grouped ncclSend / ncclRecv enqueued from C++).  Same visiting order (the shard of rank - s at step
+                # s) and the same kernel calls as the Python ring above -> bit-identical; a second call reuses the
+                # workspace; a one-buffer workspace forces every exchange to wait for the step before it.
+                ws = fa.RingWorkspace(qs.shape, world, qs.device)
+                native = fa.ring_forward(qs, ks, vs, scale, workspace=ws)
+                again = fa.ring_forward(qs, ks, vs, scale, workspace=ws)
+                tight = fa.ring_forward(qs, ks, vs, scale, depth=1)
+                torch.cuda.synchronize()
+                assert torch.equal(native, out) and torch.equal(again, out) and torch.equal(tight, out)
+                out = native
             if mode == "pull":
                 # the same ring with every K/V shard peer-mapped and pulled from its owner by the copy engines:
                 # same visiting order, same kernel calls -> bit-identical to the NCCL exchange
@@ -62,7 +76,8 @@ def _worker(rank, world, port, mode, q, k, v, scale, out_path):
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
 @pytest.mark.parametrize("mode,shape", [("bh", (2, 5, 640, 128)), ("ring", (1, 4, 1024, 128)), ("ring", (2, 2, 768, 64)),
-                                        ("pull", (1, 4, 1024, 128)), ("pull", (2, 3, 512, 64))])
+                                        ("pull", (1, 4, 1024, 128)), ("pull", (2, 3, 512, 64)),
+                                        ("native", (1, 4, 1024, 128)), ("native", (2, 3, 768, 64)), ("native", (1, 2, 4096, 128))])
 def test_two_gpu_paths_match_oracle(tmp_path, oracle, mode, shape):
     B, H, N, D = shape
     rng = np.random.default_rng(5)

@@ -1,6 +1,6 @@
 """CPU tests of the multi-GPU plumbing: (b,h) shard arithmetic, and the ring / context-parallel
 schedule + merge run as 2 gloo ranks with a torch fp32 implementation of the `fa_forward_partial`
-contract injected (the CUDA step itself is covered by tests/test_gpu_ring.py)."""
+contract injected (the CUDA step itself is covered by tests/test_gpu_ring_host.py and, on 2 GPUs, tests/test_gpu_multi.py)."""
 import os
 import socket
 
