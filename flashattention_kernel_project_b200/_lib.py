@@ -36,6 +36,7 @@ SIGNATURES = {
     "fa_last_debug": (c_int, [ctypes.POINTER(ctypes.c_uint), c_int]),
     "fa_launch_count": (ctypes.c_ulonglong, []),
     "fa_plan_segments": (c_int, [c_int] * 5 + [ctypes.POINTER(c_int), c_int]),
+    "fa_set_tail_split": (c_int, [c_int]),
     "fa_map_cache_stats": (c_int, [ctypes.POINTER(ctypes.c_ulonglong)] * 2),
 }
 

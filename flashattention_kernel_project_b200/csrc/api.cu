@@ -249,12 +249,14 @@ struct FaCall {
 struct FaPlan {
   int items_full, tail_items, tail_ctas;
 };
+std::atomic<int> g_tail_split{-1};  // -1: the environment decides (FA_TAIL_SPLIT, default on); 0 / 1: fa_set_tail_split
 bool tail_split_enabled() {
-  static const bool on = [] {
+  static const bool env_on = [] {
     const char* e = std::getenv("FA_TAIL_SPLIT");
     return e == nullptr || std::atoi(e) != 0;
   }();
-  return on;
+  const int v = g_tail_split.load(std::memory_order_relaxed);
+  return v < 0 ? env_on : v != 0;
 }
 int tail_split_cost() {  // key-tile iterations charged to a cut span for its prologue and merge (FA_TAIL_COST, default 2)
   static const int cost = [] {
@@ -269,7 +271,8 @@ FaPlan fa_plan(long long items, int nkv_tiles, int sms, bool have_pool) {
   const long long rest = items % sms;
   if (rest == 0) return plan;
   const long long total = rest * nkv_tiles;         // key-tile iterations of the partial wave
-  long long n = total / 2 < sms ? total / 2 : sms;  // spans of at least two key tiles
+  long long n = total / 2 < sms ? total / 2 : sms;  // spans of at least two key tiles ...
+  if (n > rest * 8) n = rest * 8;                   // ... and at most 8 parts per item (the merge reads every part)
   if (n <= rest) return plan;
   const long long span = (total + n - 1) / n;
   if (span + tail_split_cost() >= nkv_tiles) return plan;
@@ -1032,6 +1035,11 @@ int fa_plan_segments(int B, int H, int Nq, int Nkv, int sms, int* out, int max_s
     }
   }
   return n;
+}
+
+int fa_set_tail_split(int mode) {
+  const int before = g_tail_split.exchange(mode < 0 ? -1 : (mode != 0 ? 1 : 0), std::memory_order_relaxed);
+  return before;
 }
 
 int fa_map_cache_stats(unsigned long long* hits, unsigned long long* misses) {

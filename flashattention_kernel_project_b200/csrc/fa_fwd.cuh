@@ -78,7 +78,7 @@ struct FaCfg {
   static constexpr int kOffSum = kOffFac + 2 * 128 * 4;          // float[2][128] final l
   static constexpr int kOffBar = kOffSum + 2 * 128 * 4;
   static constexpr int kPChunks = 2;                    // P is published in two chunks: keys [0, 16*kSplitGroups), then the rest
-  static constexpr int kNumBars = 2 + 2 * kStages + 8 + 2 * kPChunks;
+  static constexpr int kNumBars = 2 + 2 * kStages + 8 + 2 * kPChunks + 2;  // + merge_full[2] (stream-K tail)
   static constexpr int kOffTmem = kOffBar + kNumBars * 8;
   static constexpr int kSmemBytes = kOffTmem + 16;
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
@@ -87,7 +87,7 @@ struct FaCfg {
 // mbarrier wait sites (reported through the debug channel on a timeout)
 enum : uint32_t {
   SITE_TMA_EMPTY = 1, SITE_MMA_QFULL, SITE_MMA_KVFULL, SITE_MMA_PFULL,
-  SITE_SM_SFULL, SITE_SM_CORR, SITE_CO_STATS, SITE_CO_LFULL, SITE_CO_OFULL
+  SITE_SM_SFULL, SITE_SM_CORR, SITE_CO_STATS, SITE_CO_LFULL, SITE_CO_OFULL, SITE_CO_MERGE
 };
 
 constexpr float kLazyRescaleTau = 8.0f;  // log2 units: P stays below 2^8, far inside fp16 range
@@ -179,7 +179,7 @@ __host__ __device__ __forceinline__ bool fa_segment(const FaParams& p, int nkv_t
 }
 
 // (Re-)arms every mbarrier of the CTA; one thread, between two CTA-wide barriers.  Layout as in the kernel:
-// q_full[2], kv_full[S], kv_empty[S], s_full[2], p_full[2][chunks], stats_full[2], o_full[2], l_full[2].
+// q_full[2], kv_full[S], kv_empty[S], s_full[2], p_full[2][chunks], stats_full[2], o_full[2], l_full[2], merge_full[2].
 template <int D>
 __device__ __forceinline__ void fa_init_barriers(uint64_t* bars, bool reinit) {
   using Cfg = FaCfg<D>;
@@ -194,6 +194,7 @@ __device__ __forceinline__ void fa_init_barriers(uint64_t* bars, bool reinit) {
   for (int i = 0; i < 2; ++i) mbar_init(b++, 4);  // stats_full
   for (int i = 0; i < 2; ++i) mbar_init(b++, 1);  // o_full
   for (int i = 0; i < 2; ++i) mbar_init(b++, 4);  // l_full
+  for (int i = 0; i < 2; ++i) mbar_init(b++, 1);  // merge_full
   fence_mbar_init();
 }
 // Between two segments of a tail CTA: every role has finished the previous segment (the epilogue's TMA store has read
@@ -228,6 +229,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
   uint64_t* const stats_full = p_full + 2 * Cfg::kPChunks;  // [2]  softmax -> correction : factors
   uint64_t* const o_full = stats_full + 2;                // [2]  MMA -> correction : last PV done
   uint64_t* const l_full = o_full + 2;                    // [2]  softmax -> correction : final l
+  uint64_t* const merge_full = l_full + 2;                // [2]  bulk copy -> correction : a parked part landed (tail merge)
   uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(smem + Cfg::kOffTmem);  // [0] TMEM base, [1] merge verdict
 
   const int warp = threadIdx.x >> 5;
@@ -236,6 +238,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
 #define FA_ROLE_COMMON()                                            \
   const int lane = threadIdx.x & 31;                                \
   const int cta = blockIdx.x;                                       \
+  const uint32_t tmem_base = *tmem_slot;                            \
   const int nkv_tiles = (p.nkv + Cfg::kKT - 1) / Cfg::kKT
 
   // ------------------------------- one-time setup -------------------------------------
@@ -256,7 +259,6 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 8) {
     // =============================== softmax warpgroups ===============================
@@ -478,7 +480,11 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
       }
 
       // ---- a partial segment parks its state; the part that arrives last merges them all ----
+      // Slot layout (floats): tile 0 block, tile 1 block, m[256], l[256]; a tile block is D/4 x 128 float4, index
+      // (column quad) * 128 + row: consecutive lanes are consecutive float4 on the way out (coalesced) and, after a
+      // 1-D bulk copy of the whole block into shared memory, on the way back in (conflict-free).
       if (seg.slot >= 0) {
+        constexpr int kTileFloats = D * 128;
         float* const slot = p.ws + (static_cast<size_t>(cta - p.items_full) * 2 + seg.slot) * kSlotFloats;
         for (int i = 0; i < ntile; ++i) {
           mbar_wait(&l_full[i], 0, dbg, SITE_CO_LFULL, i);
@@ -486,8 +492,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
           tc_fence_after();
           const uint32_t t_o = tmem_base + lane_base + (i == 0 ? Cfg::kColO0 : Cfg::kColO1);
           const int ri = i * 128 + row;
-          __stcg(slot + D * 256 + ri, fac_smem[ri]);
-          __stcg(slot + D * 256 + 256 + ri, sum_smem[ri]);
+          __stcg(slot + 2 * kTileFloats + ri, fac_smem[ri]);
+          __stcg(slot + 2 * kTileFloats + 256 + ri, sum_smem[ri]);
+          float4* const block = reinterpret_cast<float4*>(slot + i * kTileFloats);
 #pragma unroll 1
           for (int cc = 0; cc < D / 32; ++cc) {
             uint32_t o[32];
@@ -495,7 +502,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
             tmem_wait_ld();
 #pragma unroll
             for (int k4 = 0; k4 < 8; ++k4)
-              __stcg(reinterpret_cast<float4*>(slot) + (cc * 8 + k4) * 256 + ri,
+              __stcg(block + (cc * 8 + k4) * 128 + row,
                      make_float4(__uint_as_float(o[4 * k4]), __uint_as_float(o[4 * k4 + 1]),
                                  __uint_as_float(o[4 * k4 + 2]), __uint_as_float(o[4 * k4 + 3])));
           }
@@ -504,54 +511,85 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
         // the item (slot 0), the first one does so only if its span begins exactly at the item
         const int item_begin = seg.tail_item * nkv_tiles;
         const int part_first = fa_span_owner(p, nkv_tiles, item_begin);
-        const int part_last = fa_span_owner(p, nkv_tiles, item_begin + nkv_tiles - 1);
+        const int nparts = fa_span_owner(p, nkv_tiles, item_begin + nkv_tiles - 1) - part_first + 1;
         const int first_slot = fa_span_begin(p, nkv_tiles, part_first) == item_begin ? 0 : 1;
         __threadfence();
         named_bar_sync(1, 128);
         if (warp == 8 && lane == 0) {
           const unsigned int arrived = atomicAdd(p.ws_count + seg.tail_item, 1u);
-          tmem_slot[1] = (arrived == static_cast<unsigned int>(part_last - part_first)) ? 1u : 0u;
+          tmem_slot[1] = (arrived == static_cast<unsigned int>(nparts - 1)) ? 1u : 0u;
           __threadfence();
         }
         named_bar_sync(1, 128);
         if (tmem_slot[1] == 0u) continue;  // another CTA finishes this item
-        // Last to arrive: reduce all parts, in span order (the same arithmetic whichever CTA does it), into this
-        // CTA's own O accumulator and statistics, then fall through to the ordinary epilogue.
-        for (int i = 0; i < ntile; ++i) {
-          const uint32_t t_o = tmem_base + lane_base + (i == 0 ? Cfg::kColO0 : Cfg::kColO1);
+        // Last to arrive: reduce ALL parts (its own included: the same arithmetic whichever CTA ends up here), in span
+        // order, into this CTA's O accumulator in TMEM and its statistics, then fall through to the ordinary epilogue.
+        // The parts come back through 1-D bulk copies into the idle K/V ring, double-buffered: part j + 1 is in
+        // flight while part j is accumulated.
+        auto part_slot = [&](int k) {
+          return p.ws + (static_cast<size_t>(part_first + k) * 2 + (k == 0 ? first_slot : 0)) * kSlotFloats;
+        };
+        const int steps = ntile * nparts;
+        auto fetch = [&](int j) {  // one thread
+          const int b = j & 1;
+          mbar_arrive_expect_tx(&merge_full[b], kTileFloats * 4);
+          bulk_copy_g2s(kv_smem + b * (kTileFloats * 4), part_slot(j % nparts) + (j / nparts) * kTileFloats, kTileFloats * 4,
+                        &merge_full[b]);
+        };
+        if (warp == 8) {  // whole warp, elected lane: a bulk copy under `lane == 0` gets a per-thread serialisation loop
+          if (elect_one()) {
+            fence_proxy_async_all();
+            fetch(0);
+          }
+          __syncwarp();
+        }
+        float m_all = 0.f, l_all = 0.f;
+        for (int j = 0; j < steps; ++j) {
+          const int i = j / nparts, k = j - i * nparts;
           const int ri = i * 128 + row;
-          float m_all = -INFINITY;
-          for (int t = part_first; t <= part_last; ++t) {
-            const float* const ps = p.ws + (static_cast<size_t>(t) * 2 + (t == part_first ? first_slot : 0)) * kSlotFloats;
-            m_all = fmaxf(m_all, __ldcg(ps + D * 256 + ri));
+          const uint32_t t_o = tmem_base + lane_base + (i == 0 ? Cfg::kColO0 : Cfg::kColO1);
+          if (warp == 8 && j + 1 < steps) {  // the buffer of step j + 1 was released at the end of step j - 1
+            if (elect_one()) fetch(j + 1);
+            __syncwarp();
           }
-          float l_all = 0.f;
-          for (int t = part_first; t <= part_last; ++t) {
-            const float* const ps = p.ws + (static_cast<size_t>(t) * 2 + (t == part_first ? first_slot : 0)) * kSlotFloats;
-            l_all = fmaf(__ldcg(ps + D * 256 + 256 + ri), ex2_approx((__ldcg(ps + D * 256 + ri) - m_all) * c_abs), l_all);
+          if (k == 0) {
+            m_all = -INFINITY;
+            for (int kk = 0; kk < nparts; ++kk) m_all = fmaxf(m_all, __ldcg(part_slot(kk) + 2 * kTileFloats + ri));
+            l_all = 0.f;
+            for (int kk = 0; kk < nparts; ++kk) {
+              const float* const ps = part_slot(kk) + 2 * kTileFloats;
+              l_all = fmaf(__ldcg(ps + 256 + ri), ex2_approx((__ldcg(ps + ri) - m_all) * c_abs), l_all);
+            }
           }
+          const float w = ex2_approx((__ldcg(part_slot(k) + 2 * kTileFloats + ri) - m_all) * c_abs);
+          mbar_wait(&merge_full[j & 1], (j >> 1) & 1, dbg, SITE_CO_MERGE, j);
+          const float4* const src = reinterpret_cast<const float4*>(kv_smem + (j & 1) * (kTileFloats * 4));
 #pragma unroll 1
           for (int cc = 0; cc < D / 32; ++cc) {
-            float v[32];
+            uint32_t o[32];
+            if (k > 0) {
+              tmem_ld_x32(t_o + cc * 32, o);
+              tmem_wait_ld();
+            } else {
 #pragma unroll
-            for (int k = 0; k < 32; ++k) v[k] = 0.f;
-            for (int t = part_first; t <= part_last; ++t) {
-              const float* const ps = p.ws + (static_cast<size_t>(t) * 2 + (t == part_first ? first_slot : 0)) * kSlotFloats;
-              const float w = ex2_approx((__ldcg(ps + D * 256 + ri) - m_all) * c_abs);
-#pragma unroll
-              for (int k4 = 0; k4 < 8; ++k4) {
-                const float4 a = __ldcg(reinterpret_cast<const float4*>(ps) + (cc * 8 + k4) * 256 + ri);
-                v[4 * k4 + 0] = fmaf(a.x, w, v[4 * k4 + 0]);
-                v[4 * k4 + 1] = fmaf(a.y, w, v[4 * k4 + 1]);
-                v[4 * k4 + 2] = fmaf(a.z, w, v[4 * k4 + 2]);
-                v[4 * k4 + 3] = fmaf(a.w, w, v[4 * k4 + 3]);
-              }
+              for (int e = 0; e < 32; ++e) o[e] = 0u;
             }
-            tmem_st_x32(t_o + cc * 32, reinterpret_cast<const uint32_t*>(v));
+#pragma unroll
+            for (int k4 = 0; k4 < 8; ++k4) {
+              const float4 a = src[(cc * 8 + k4) * 128 + row];
+              o[4 * k4 + 0] = __float_as_uint(fmaf(a.x, w, __uint_as_float(o[4 * k4 + 0])));
+              o[4 * k4 + 1] = __float_as_uint(fmaf(a.y, w, __uint_as_float(o[4 * k4 + 1])));
+              o[4 * k4 + 2] = __float_as_uint(fmaf(a.z, w, __uint_as_float(o[4 * k4 + 2])));
+              o[4 * k4 + 3] = __float_as_uint(fmaf(a.w, w, __uint_as_float(o[4 * k4 + 3])));
+            }
+            tmem_st_x32(t_o + cc * 32, o);
           }
           tmem_wait_st();
-          sum_smem[ri] = l_all;  // read back below by this same thread
-          fac_smem[ri] = m_all;
+          if (k == nparts - 1) {
+            sum_smem[ri] = l_all;  // read back below by this same thread
+            fac_smem[ri] = m_all;
+          }
+          named_bar_sync(1, 128);  // every thread is done with buffer j & 1
         }
       }
 
@@ -643,11 +681,17 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
         if (emit_f16) {
           fence_proxy_async_smem();
           named_bar_sync(1, 128);
-          if (warp == 8 && lane == 0) {
+          if (warp == 8) {
+            // warp-uniform coordinates (a shuffle from lane 0 is what lets ptxas issue the TMA store without a
+            // per-thread serialisation loop); lane 0 owns the bulk group it later waits on
+            const int row0 = __shfl_sync(0xffffffffu, q0 + i * 128, 0), bh_u = __shfl_sync(0xffffffffu, bh, 0);
+            const uint8_t* const stage_u = q_smem + __shfl_sync(0xffffffffu, i, 0) * Cfg::kTileBytes;
+            if (lane == 0) {
 #pragma unroll
-            for (int b = 0; b < Cfg::kBoxes; ++b)
-              tma_store_3d(&mapO, stage + b * Cfg::kBoxBytes, b * 64, q0 + i * 128, bh);  // clips rows >= nq
-            tma_store_commit();
+              for (int b = 0; b < Cfg::kBoxes; ++b)
+                tma_store_3d(&mapO, stage_u + b * Cfg::kBoxBytes, b * 64, row0, bh_u);  // clips rows >= nq
+              tma_store_commit();
+            }
           }
         }
       }
@@ -662,7 +706,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
     // execute in order, which gives PV_i(j) before QK_i(j+1) (whose S overwrites P_i) for free.
     // (Two issuing warps, one per tile, were measured slower: the tiles' MMAs interleave on the pipe
     //  and lengthen each tile's S -> softmax -> P chain.)
-    setmaxnreg_dec<64>();
+    setmaxnreg_dec<48>();
     {
       FA_ROLE_COMMON();
       constexpr uint32_t idesc_qk = umma_idesc_f16(128, 128, 0, 0);
@@ -788,14 +832,14 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
       }
     }
   } else {
-    setmaxnreg_dec<32>();
+    setmaxnreg_dec<48>();
   }
 
   // ---------------------------------- teardown ----------------------------------------
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 8) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  if (warp == 8) tmem_dealloc(*tmem_slot, Cfg::kTmemCols);
 #undef FA_ROLE_COMMON
 }
 

@@ -234,9 +234,13 @@ unsigned long long fa_launch_count(void);
  * parts of an item are merged with the (m, l, O) rule of Streaming_FlashAttention_Forward_Kernel/flashattn_streaming_16x16.cu:247-261).
  * Writes up to max_segments rows {cta, item, kv_tile_begin, kv_tile_end, slot, tail_item} (slot -1 = whole item)
  * into `out` (may be NULL) and returns the number of segments, or a negative FA_ERR_*.
- * Environment FA_TAIL_SPLIT=0 (read once) disables the cut.
+ * Environment FA_TAIL_SPLIT=0 (read once) disables the cut; fa_set_tail_split(0 / 1) overrides the environment for
+ * the process, fa_set_tail_split(-1) hands the decision back to it; the previous setting is returned.  A cut item
+ * is summed in a different order than a whole one (its parts are merged with the (m, l, O) rule), so a (b,h) slice
+ * is bit-identical to the same slice of a larger batch only when both are decomposed alike -- e.g. with the cut off.
  */
 int fa_plan_segments(int B, int H, int Nq, int Nkv, int sms, int* out, int max_segments);
+int fa_set_tail_split(int mode);
 
 /* Tensor-map cache counters (the cache is bounded and mutex-protected); returns its capacity. */
 int fa_map_cache_stats(unsigned long long* hits, unsigned long long* misses);
