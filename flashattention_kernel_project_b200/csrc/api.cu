@@ -9,6 +9,7 @@
 #include <dlfcn.h>
 
 #include <atomic>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -243,9 +244,18 @@ struct FaCall {
   int mode, is_first, is_last;
 };
 
-// How the grid is cut (fa_fwd.cuh, FaSegment).  Items beyond the last full wave of `sms` CTAs are cut along K/V into
-// equal spans, one per SM, when that shortens the last wave: whole items cost nkv_tiles iterations each, a span costs
-// its length plus about two iterations of prologue and merge.
+// How the grid is cut (fa_fwd.cuh, FaSegment).  The kernel can cut the items of a partial last wave along K/V into
+// equal spans of key tiles ("stream-K"); when that pays was measured on B200 (scripts/tail_split_ab.py, both settings
+// interleaved in one process, CUDA-graph time):
+//   * multi-wave grids (BASELINE configs 2-4, 256 ... 8192 items on 148 SMs): the cut is neutral to 2.6 % SLOWER --
+//     the part is power-capped, so the SMs that do run the partial last wave clock higher while the others idle, and
+//     512 whole items (3.46 waves, config 3 on 8 GPUs) already take 3.5 item-times, not 4;
+//   * grids that fill less than half the SMs (small batch x long sequence, e.g. one (b,h) of N = 4096: 16 items):
+//     1.3-1.6x faster, limited by the merge, which costs the last CTA of an item about 2.2 key-tile iterations per
+//     part (two 64 KB bulk copies + accumulate).
+// So only sub-half-wave grids are cut, into p parts per item with p ~ sqrt(L / 2.2) minimising L/p + 2.2 p
+// (L = key tiles per item), 2 <= p <= min(8, SMs / items), spans of at least 4 key tiles, and only if the model
+// says the cut wins.  FA_TAIL_COST (default 3) is the fixed cost of a cut span in key-tile iterations.
 struct FaPlan {
   int items_full, tail_items, tail_ctas;
 };
@@ -258,27 +268,28 @@ bool tail_split_enabled() {
   const int v = g_tail_split.load(std::memory_order_relaxed);
   return v < 0 ? env_on : v != 0;
 }
-int tail_split_cost() {  // key-tile iterations charged to a cut span for its prologue and merge (FA_TAIL_COST, default 2)
+int tail_split_cost() {
   static const int cost = [] {
     const char* e = std::getenv("FA_TAIL_COST");
-    return e != nullptr ? std::atoi(e) : 2;
+    return e != nullptr ? std::atoi(e) : 3;
   }();
   return cost;
 }
 FaPlan fa_plan(long long items, int nkv_tiles, int sms, bool have_pool) {
   FaPlan plan{static_cast<int>(items), 0, 0};
   if (!have_pool || !tail_split_enabled() || sms <= 0) return plan;
-  const long long rest = items % sms;
-  if (rest == 0) return plan;
-  const long long total = rest * nkv_tiles;         // key-tile iterations of the partial wave
-  long long n = total / 2 < sms ? total / 2 : sms;  // spans of at least two key tiles ...
-  if (n > rest * 8) n = rest * 8;                   // ... and at most 8 parts per item (the merge reads every part)
-  if (n <= rest) return plan;
-  const long long span = (total + n - 1) / n;
-  if (span + tail_split_cost() >= nkv_tiles) return plan;
+  if (items * 2 > sms) return plan;  // at least half a wave: leave it whole (see above)
+  const double L = nkv_tiles;
+  long long p = static_cast<long long>(std::sqrt(L / 2.2) + 0.5);
+  const long long p_max = sms / items < 8 ? sms / items : 8;
+  if (p > p_max) p = p_max;
+  if (p > nkv_tiles / 4) p = nkv_tiles / 4;
+  if (p < 2) return plan;
+  if (L / p + tail_split_cost() + 2.2 * p >= L) return plan;
+  const long long total = items * nkv_tiles, n = items * p;
   if ((total + 1) * n >= 0x7fffffffll) return plan;  // the kernel's span arithmetic is 32-bit
-  plan.items_full = static_cast<int>(items - rest);
-  plan.tail_items = static_cast<int>(rest);
+  plan.items_full = 0;
+  plan.tail_items = static_cast<int>(items);
   plan.tail_ctas = static_cast<int>(n);
   return plan;
 }

@@ -804,6 +804,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
     setmaxnreg_dec<48>();
     {
       FA_ROLE_COMMON();
+      (void)tmem_base;
       FaSegment seg;
       for (int si = 0; fa_segment(p, nkv_tiles, cta, si, seg); ++si) {
         if (si > 0) fa_segment_boundary<D>(bars, warp, lane);

@@ -1,9 +1,10 @@
-"""Host-side work decomposition of the attention kernel (fa_plan_segments, no device work): the stream-K cut of the
-last wave must cover every (item, key tile) exactly once, give every tail CTA an equal span, and describe the
-parts of a cut item consistently for the writer and the merging reader (csrc/fa_fwd.cuh: FaSegment).
+"""Host-side work decomposition of the attention kernel (fa_plan_segments, no device work): the stream-K cut must
+cover every (item, key tile) exactly once, give every cut CTA an equal span, and describe the parts of a cut item
+consistently for the writer and the merging reader (csrc/fa_fwd.cuh: FaSegment).
 
-The reference's grid is one CTA per (query block, b*h) (FlashAttention/flashattn_forward_wmma/flashattn_forward_wmma_v4.cu:452);
-BASELINE config 3 head-sharded over 8 GPUs leaves 512 such items for 148 SMs, i.e. 3.46 waves."""
+The reference's grid is one CTA per (query block, b*h) (FlashAttention/flashattn_forward_wmma/flashattn_forward_wmma_v4.cu:452).
+Measured on B200 (scripts/tail_split_ab.py), cutting pays only for grids that fill less than half the SMs (small
+batch x long sequence); multi-wave grids -- all BASELINE configs -- stay whole (csrc/api.cu: fa_plan)."""
 import ctypes
 
 import numpy as np
@@ -21,9 +22,9 @@ def segments(B, H, Nq, Nkv, sms=148):
     return np.array(buf, dtype=np.int64).reshape(n, 6)
 
 
-SHAPES = [(8, 32, 4096, 4096), (1, 32, 4096, 4096), (2, 32, 4096, 4096), (4, 16, 1024, 1024), (1, 1, 128, 128),
-          (1, 1, 4096, 4096), (1, 32, 8192, 8192), (3, 5, 512, 512), (1, 2, 300, 300), (1, 7, 1000, 5000),
-          (2, 3, 257, 129), (1, 1, 65536, 65536), (5, 31, 2048, 640)]
+SHAPES = [(8, 32, 4096, 4096), (1, 32, 4096, 4096), (4, 16, 1024, 1024), (1, 1, 128, 128), (1, 1, 4096, 4096),
+          (1, 3, 2000, 2000), (2, 5, 1500, 1500), (1, 2, 777, 777), (3, 5, 512, 512), (1, 2, 300, 300), (1, 7, 1000, 5000),
+          (2, 3, 257, 129), (1, 1, 65536, 65536), (1, 5, 8192, 9999), (1, 1, 300, 70000)]
 
 
 @pytest.mark.parametrize("shape", SHAPES)
@@ -43,15 +44,12 @@ def test_every_key_tile_of_every_item_is_covered_exactly_once(shape, sms):
     assert ctas.min() == 0 and set(ctas) == set(range(ctas.max() + 1))
     tail = seg[seg[:, 4] >= 0]
     if len(tail):
-        first_tail_cta = tail[:, 0].min()
-        full = seg[seg[:, 0] < first_tail_cta]
-        assert (np.bincount(full[:, 0]) == 1).all() and (full[:, 4] == -1).all()
-        assert first_tail_cta % sms == 0  # the cut applies to the partial last wave only
-        # equal spans: the tail CTAs' work differs by at most one key tile
-        work = np.bincount(seg[seg[:, 0] >= first_tail_cta, 0] - first_tail_cta,
-                           weights=(seg[:, 3] - seg[:, 2])[seg[:, 0] >= first_tail_cta])
-        assert work.max() - work.min() <= 1 and work.min() >= 2
-        assert len(work) <= sms
+        # a cut grid is cut as a whole: equal spans (they differ by at most one key tile), at least 4 key tiles each,
+        # no more CTAs than SMs, at most 8 parts per item
+        assert items * 2 <= sms
+        work = np.bincount(seg[:, 0], weights=seg[:, 3] - seg[:, 2])
+        assert work.max() - work.min() <= 1 and work.min() >= 4 and len(work) <= sms
+        assert np.bincount(tail[:, 1]).max() <= 9
 
 
 @pytest.mark.parametrize("shape", SHAPES)
@@ -68,14 +66,25 @@ def test_parts_of_a_cut_item_use_distinct_slots_in_cta_order(shape):
         assert (np.diff(parts[:, 0]) == 1).all()            # consecutive CTAs ...
         assert (parts[1:, 2] == parts[:-1, 3]).all()        # ... over consecutive key-tile ranges
         assert (parts[1:, 4] == 0).all()                    # later parts start their span inside the item
+        assert parts[0, 2] == 0 and parts[-1, 3] == (shape[3] + 127) // 128
         assert len(np.unique(parts[:, 5])) == 1
 
 
-def test_config3_shard_of_eight_gpus_needs_fewer_than_four_waves():
-    """32 (b,h) of config 3 = 512 items on 148 SMs: 3 full waves + a cut tail of ceil(68 * 32 / 148) = 15 tiles."""
-    seg = segments(1, 32, 4096, 4096, 148)
-    work = np.bincount(seg[:, 0], weights=seg[:, 3] - seg[:, 2])
-    assert (work[:444] == 32).all() and len(work) == 444 + 148 and work[444:].max() == 15
+def test_policy_follows_the_measurements():
+    """Multi-wave grids stay whole (BASELINE configs 2, 3 -- also as the 32-(b,h) shard of 8 GPUs -- and 4); one (b,h)
+    of N = 4096 (16 items x 32 key tiles) is cut into 4 parts per item (sqrt(32 / 2.2) ~ 3.8); short sequences are
+    never cut."""
+    for shape in [(4, 16, 1024, 1024), (8, 32, 4096, 4096), (1, 32, 4096, 4096), (1, 32, 65536, 65536), (1, 32, 8192, 8192)]:
+        seg = segments(*shape)
+        assert (seg[:, 4] == -1).all() and len(seg) == shape[0] * shape[1] * ((shape[2] + 255) // 256)
+    seg = segments(1, 1, 4096, 4096)
+    assert len(seg) == 64 and (seg[:, 3] - seg[:, 2] == 8).all() and (seg[:, 4] >= 0).all()
+    seg = segments(1, 8, 1024, 1024)  # 32 items x 8 key tiles: spans would drop below 4 tiles
+    assert (seg[:, 4] == -1).all()
+    seg = segments(1, 4, 16384, 16384)  # 256 items: more than half a wave
+    assert (seg[:, 4] == -1).all()
+    seg = segments(1, 1, 16384, 16384)  # 64 items x 128 tiles, 148 // 64 = 2 parts each
+    assert len(seg) == 128 and (seg[:, 3] - seg[:, 2] == 64).all()
 
 
 def test_bad_arguments():
