@@ -259,14 +259,18 @@ struct FaCall {
 struct FaPlan {
   int items_full, tail_items, tail_ctas;
 };
-std::atomic<int> g_tail_split{-1};  // -1: the environment decides (FA_TAIL_SPLIT, default on); 0 / 1: fa_set_tail_split
-bool tail_split_enabled() {
-  static const bool env_on = [] {
+// -1: the environment decides (FA_TAIL_SPLIT = 0 / 1 / 2, default 1); 0: never cut; 1: cut where the model above says
+// it pays; 2: cut the partial last wave of ANY grid into equal spans, whatever the model says (the general stream-K
+// plan -- CTAs whose span straddles two items, items shared by up to 8 CTAs; used by the tests and the A/B script)
+std::atomic<int> g_tail_split{-1};
+int tail_split_mode() {
+  static const int env_mode = [] {
     const char* e = std::getenv("FA_TAIL_SPLIT");
-    return e == nullptr || std::atoi(e) != 0;
+    const int v = e == nullptr ? 1 : std::atoi(e);
+    return v < 0 || v > 2 ? 1 : v;
   }();
   const int v = g_tail_split.load(std::memory_order_relaxed);
-  return v < 0 ? env_on : v != 0;
+  return v < 0 ? env_mode : v;
 }
 int tail_split_cost() {
   static const int cost = [] {
@@ -277,7 +281,19 @@ int tail_split_cost() {
 }
 FaPlan fa_plan(long long items, int nkv_tiles, int sms, bool have_pool) {
   FaPlan plan{static_cast<int>(items), 0, 0};
-  if (!have_pool || !tail_split_enabled() || sms <= 0) return plan;
+  const int mode = tail_split_mode();
+  if (!have_pool || mode == 0 || sms <= 0) return plan;
+  if (mode == 2) {
+    const long long rest = items % sms;
+    const long long total = rest * nkv_tiles;         // key-tile iterations of the partial wave
+    long long n = total / 2 < sms ? total / 2 : sms;  // spans of at least two key tiles ...
+    if (n > rest * 8) n = rest * 8;                   // ... and at most 8 parts per item
+    if (rest == 0 || n <= rest || (total + 1) * n >= 0x7fffffffll) return plan;
+    plan.items_full = static_cast<int>(items - rest);
+    plan.tail_items = static_cast<int>(rest);
+    plan.tail_ctas = static_cast<int>(n);
+    return plan;
+  }
   if (items * 2 > sms) return plan;  // at least half a wave: leave it whole (see above)
   const double L = nkv_tiles;
   long long p = static_cast<long long>(std::sqrt(L / 2.2) + 0.5);
@@ -1049,7 +1065,7 @@ int fa_plan_segments(int B, int H, int Nq, int Nkv, int sms, int* out, int max_s
 }
 
 int fa_set_tail_split(int mode) {
-  const int before = g_tail_split.exchange(mode < 0 ? -1 : (mode != 0 ? 1 : 0), std::memory_order_relaxed);
+  const int before = g_tail_split.exchange(mode < 0 ? -1 : (mode > 2 ? 2 : mode), std::memory_order_relaxed);
   return before;
 }
 

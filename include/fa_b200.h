@@ -234,8 +234,9 @@ unsigned long long fa_launch_count(void);
  * parts of an item are merged with the (m, l, O) rule of Streaming_FlashAttention_Forward_Kernel/flashattn_streaming_16x16.cu:247-261).
  * Writes up to max_segments rows {cta, item, kv_tile_begin, kv_tile_end, slot, tail_item} (slot -1 = whole item)
  * into `out` (may be NULL) and returns the number of segments, or a negative FA_ERR_*.
- * Environment FA_TAIL_SPLIT=0 (read once) disables the cut; fa_set_tail_split(0 / 1) overrides the environment for
- * the process, fa_set_tail_split(-1) hands the decision back to it; the previous setting is returned.  A cut item
+ * Environment FA_TAIL_SPLIT (read once): 0 never cuts, 1 (default) cuts where measurements say it pays (grids that
+ * fill less than half the SMs), 2 cuts the partial last wave of any grid.  fa_set_tail_split(0 / 1 / 2) overrides the
+ * environment for the process, fa_set_tail_split(-1) hands the decision back to it; the previous setting is returned.  A cut item
  * is summed in a different order than a whole one (its parts are merged with the (m, l, O) rule), so a (b,h) slice
  * is bit-identical to the same slice of a larger batch only when both are decomposed alike -- e.g. with the cut off.
  */

@@ -166,17 +166,17 @@ def test_config3_sampled_rows_and_properties(fa, oracle):
 
 def test_cut_items_match_whole_items(fa, oracle):
     """The stream-K cut of the last wave against the uncut kernel on shapes whose items are cut into 2 ... many parts
-    (few items x many key tiles), with ragged query blocks and a partial last key tile, all output modes: same
-    result within the fp16 rounding of the output (fp32 output: 1e-5 relative), and both within tolerance of the
-    oracle.  The merge is the (m, l, O) rule of Streaming_.../flashattn_streaming_16x16.cu:247-261 applied to parts."""
+    (few items x many key tiles), with ragged query blocks and a partial last key tile, fp16 and fp32 output: the
+    same result up to the fp16 rounding of P, and within tolerance of the oracle.  The merge is the (m, l, O) rule of Streaming_.../flashattn_streaming_16x16.cu:247-261 applied to parts."""
     lib = fa.load_library()
-    for (B, H, N, D) in [(1, 1, 4096, 128), (1, 3, 2000, 64), (2, 5, 1500, 128), (1, 8, 1024, 64), (1, 2, 777, 128)]:
+    # mode 2 cuts the partial last wave of any grid: also exercises CTAs whose span straddles two items (160 items)
+    for (B, H, N, D) in [(1, 1, 4096, 128), (1, 3, 2000, 64), (2, 5, 1500, 128), (1, 5, 8192, 64), (1, 2, 777, 128)]:
         q, k, v = (torch.from_numpy(x).cuda() for x in _inputs(B, H, N, D, dist="normal", seed=N + B, std=1.5))
         scale = 1.0 / np.sqrt(D)
-        n = lib.fa_plan_segments(B, H, N, N, torch.cuda.get_device_properties(0).multi_processor_count, None, 0)
         items = B * H * ((N + 255) // 256)
-        before = lib.fa_set_tail_split(1)
+        before = lib.fa_set_tail_split(2)
         try:
+            n = lib.fa_plan_segments(B, H, N, N, torch.cuda.get_device_properties(0).multi_processor_count, None, 0)
             cut16, cut32 = fa.fa_forward(q, k, v, scale), fa.fa_forward_f32out(q, k, v, scale)
             lib.fa_set_tail_split(0)
             whole16, whole32 = fa.fa_forward(q, k, v, scale), fa.fa_forward_f32out(q, k, v, scale)
@@ -184,8 +184,10 @@ def test_cut_items_match_whole_items(fa, oracle):
             lib.fa_set_tail_split(before)
         torch.cuda.synchronize()
         assert n > items, "this shape was meant to exercise the cut"
-        assert (cut32 - whole32).abs().max().item() <= 1e-5 * max(1.0, whole32.abs().max().item())
-        assert (cut16.float() - whole16.float()).abs().max().item() <= whole16.float().abs().max().item() * 2.0 ** -10
+        # each part rounds P = exp2(s - m_part) to fp16 against ITS running max, so cut and whole carry independent
+        # fp16-P rounding noise (~3e-4 rel-L2 each against the exact result): compare at that level
+        for cut, whole in ((cut32, whole32), (cut16.float(), whole16.float())):
+            assert oracle.rel_l2(cut.cpu().numpy(), whole.cpu().numpy()) <= 6e-4
         ref = oracle.attention_f16(*(x.cpu().numpy().reshape(B * H, N, D) for x in (q, k, v)), scale)
         _check(oracle, cut16.float().cpu().numpy().reshape(B * H, N, D), ref)
         _check(oracle, cut32.cpu().numpy().reshape(B * H, N, D), ref, rel_tol=5e-4)

@@ -13,12 +13,17 @@ import pytest
 import flashattention_kernel_project_b200 as fa
 
 
-def segments(B, H, Nq, Nkv, sms=148):
+def segments(B, H, Nq, Nkv, sms=148, mode=1):
+    """mode 1: the shipped policy; mode 2: the general stream-K plan (partial last wave of any grid cut)."""
     lib = fa.load_library()
-    n = lib.fa_plan_segments(B, H, Nq, Nkv, sms, None, 0)
-    assert n > 0
-    buf = (ctypes.c_int * (6 * n))()
-    assert lib.fa_plan_segments(B, H, Nq, Nkv, sms, buf, n) == n
+    before = lib.fa_set_tail_split(mode)
+    try:
+        n = lib.fa_plan_segments(B, H, Nq, Nkv, sms, None, 0)
+        assert n > 0
+        buf = (ctypes.c_int * (6 * n))()
+        assert lib.fa_plan_segments(B, H, Nq, Nkv, sms, buf, n) == n
+    finally:
+        lib.fa_set_tail_split(before)
     return np.array(buf, dtype=np.int64).reshape(n, 6)
 
 
@@ -29,9 +34,10 @@ SHAPES = [(8, 32, 4096, 4096), (1, 32, 4096, 4096), (4, 16, 1024, 1024), (1, 1, 
 
 @pytest.mark.parametrize("shape", SHAPES)
 @pytest.mark.parametrize("sms", [148, 132, 7])
-def test_every_key_tile_of_every_item_is_covered_exactly_once(shape, sms):
+@pytest.mark.parametrize("mode", [1, 2])
+def test_every_key_tile_of_every_item_is_covered_exactly_once(shape, sms, mode):
     B, H, Nq, Nkv = shape
-    seg = segments(B, H, Nq, Nkv, sms)
+    seg = segments(B, H, Nq, Nkv, sms, mode)
     items, tiles = B * H * ((Nq + 255) // 256), (Nkv + 127) // 128
     cover = np.zeros((items, tiles), dtype=np.int64)
     for cta, item, k0, k1, slot, tail_item in seg:
@@ -43,21 +49,30 @@ def test_every_key_tile_of_every_item_is_covered_exactly_once(shape, sms):
     ctas = seg[:, 0]
     assert ctas.min() == 0 and set(ctas) == set(range(ctas.max() + 1))
     tail = seg[seg[:, 4] >= 0]
-    if len(tail):
+    if len(tail) and mode == 1:
         # a cut grid is cut as a whole: equal spans (they differ by at most one key tile), at least 4 key tiles each,
         # no more CTAs than SMs, at most 8 parts per item
         assert items * 2 <= sms
         work = np.bincount(seg[:, 0], weights=seg[:, 3] - seg[:, 2])
         assert work.max() - work.min() <= 1 and work.min() >= 4 and len(work) <= sms
         assert np.bincount(tail[:, 1]).max() <= 9
+    if len(tail) and mode == 2:
+        # whole-item CTAs first (one segment each, full waves), then the cut CTAs with equal spans of >= 2 key tiles
+        first_tail_cta = tail[:, 0].min()
+        full = seg[seg[:, 0] < first_tail_cta]
+        assert (np.bincount(full[:, 0]) == 1).all() and (full[:, 4] == -1).all() and first_tail_cta % sms == 0
+        sel = seg[:, 0] >= first_tail_cta
+        work = np.bincount(seg[sel, 0] - first_tail_cta, weights=(seg[:, 3] - seg[:, 2])[sel])
+        assert work.max() - work.min() <= 1 and work.min() >= 2 and len(work) <= sms
 
 
 @pytest.mark.parametrize("shape", SHAPES)
-def test_parts_of_a_cut_item_use_distinct_slots_in_cta_order(shape):
+@pytest.mark.parametrize("mode", [1, 2])
+def test_parts_of_a_cut_item_use_distinct_slots_in_cta_order(shape, mode):
     """The merging CTA reads part t of an item from slot 1 of tail CTA t only if that CTA's span began in an earlier
     item (then it is the item's first part), else from slot 0: no two parts may share a (cta, slot) pair, and the
     parts of an item must be consecutive tail CTAs in key order."""
-    seg = segments(*shape)
+    seg = segments(*shape, mode=mode)
     tail = seg[seg[:, 4] >= 0]
     assert len({(c, s) for c, _, _, _, s, _ in tail}) == len(tail)
     for item in np.unique(tail[:, 1]):
