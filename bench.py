@@ -296,7 +296,7 @@ def ring_cfg4(torch, dist, fa, dev, rank, world):
     rel, mx = 0.0, 0.0
     for r in (0, world - 1):
         qr, got = qs[r][0].cpu().numpy()[None], qs[r][1].float().cpu().numpy()
-        ref = orc.attention_f16_rows(qr, k_all, v_all, scale, np.arange(qr.shape[1]))
+        ref = orc.attention_f16_rows(qr, k_all, v_all, scale, np.arange(qr.shape[1]), nthreads=os.cpu_count() or 1)
         rel, mx = max(rel, orc.rel_l2(got, ref)), max(mx, orc.max_abs(got, ref))
     fl = flops(B, H, N, D)
     return {"config": "fp16 attention fwd B=1,H=32,N=65536,D=128, sequence split over the ranks (ring / context parallel)",
