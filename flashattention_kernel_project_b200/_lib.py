@@ -22,6 +22,9 @@ SIGNATURES = {
     "fa_forward_partial": (c_int, [c_void_p] * 6 + [c_int] * 5 + [c_float, c_int, c_int, c_void_p, c_void_p]),
     "fa_ring_workspace_bytes": (ctypes.c_size_t, [c_int] * 6),
     "fa_ring_forward": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_float, c_int, c_int, c_void_p, c_void_p, ctypes.c_size_t, c_void_p]),
+    "fa_enable_peer_access": (c_int, [c_int]),
+    "fa_ring_forward_pull": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_float, c_int, c_int, ctypes.POINTER(c_void_p),
+                                     ctypes.POINTER(c_void_p), c_void_p, ctypes.c_size_t, c_void_p]),
     "gemm_fused_epilogue": (c_int, [c_void_p] * 5 + [c_int] * 3 + [c_void_p]),
     "gemm_fused_epilogue_act": (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_void_p]),
     "gemm_batched_strided": (c_int, [c_void_p] * 3 + [c_int] * 4 + [ctypes.c_longlong] * 6 + [c_int, c_float, c_void_p]),

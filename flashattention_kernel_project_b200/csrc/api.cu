@@ -808,6 +808,85 @@ int fa_ring_forward(const void* Q, const void* K, const void* V, void* O, int B,
   return FA_OK;
 }
 
+int fa_enable_peer_access(int peer_device) {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return FA_ERR_NO_DEVICE;
+  }
+  if (peer_device == dev) return FA_OK;
+  int can = 0;
+  cudaError_t e = cudaDeviceCanAccessPeer(&can, dev, peer_device);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return static_cast<int>(e);
+  }
+  if (!can) return FA_ERR_BAD_ARGUMENT;
+  e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) {
+    (void)cudaGetLastError();
+    return FA_OK;
+  }
+  return e == cudaSuccess ? FA_OK : static_cast<int>(e);
+}
+
+int fa_ring_forward_pull(const void* Q, const void* K, const void* V, void* O, int B, int H, int n, int D, float scale,
+                         int rank, int world, const void* const* peer_k, const void* const* peer_v, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  if (B <= 0 || H <= 0 || n <= 0) return FA_ERR_BAD_SHAPE;
+  if (D != 64 && D != 128) return FA_ERR_BAD_HEAD_DIM;
+  if (world <= 0 || world > kMaxRingWorld || rank < 0 || rank >= world) return FA_ERR_BAD_ARGUMENT;
+  if (Q == nullptr || K == nullptr || V == nullptr || O == nullptr || workspace == nullptr) return FA_ERR_NULL_POINTER;
+  if (world > 1 && (peer_k == nullptr || peer_v == nullptr)) return FA_ERR_NULL_POINTER;
+  for (int r = 0; r < world && world > 1; ++r)
+    if (r != rank && (peer_k[r] == nullptr || peer_v[r] == nullptr)) return FA_ERR_NULL_POINTER;
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255u) != 0) return FA_ERR_MISALIGNED;
+  const RingLayout L = ring_layout(B, H, n, D, world, workspace_bytes);
+  if (workspace_bytes < L.kv || (world > 1 && L.depth < 1)) return FA_ERR_BAD_ARGUMENT;
+  DeviceState* st = nullptr;
+  int rc = current_device_state(&st);
+  if (rc != FA_OK) return rc;
+  char* const ws = static_cast<char*>(workspace);
+  float* const o_acc = reinterpret_cast<float*>(ws + L.state_o);
+  float* const m = reinterpret_cast<float*>(ws + L.state_m);
+  float* const l = reinterpret_cast<float*>(ws + L.state_l);
+  const cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (world == 1) return fa_forward_partial(Q, K, V, o_acc, m, l, B, H, n, n, D, scale, 1, 1, O, stream);
+  if ((rc = ring_init(st)) != FA_OK) return rc;
+  std::lock_guard<std::mutex> ring_lock(st->host_mu);
+  const size_t bytes = static_cast<size_t>(B) * H * n * D * 2;
+  const int depth = L.depth;
+  auto kbuf = [&](int slot) { return ws + L.kv + static_cast<size_t>(slot) * 2 * L.shard_bytes; };
+  // Fetch x: the shard of rank - x, copied by THIS GPU's copy engines straight out of its owner's memory (peer
+  // mapping over NVLink / NVSwitch): no SM is taken from the attention kernel, no rank synchronises with another.
+  auto fetch = [&](int x) -> int {
+    const int from = (rank - x + world) % world;
+    char* const dst = kbuf((x - 1) % depth);
+    FA_CUDA_TRY(cudaMemcpyAsync(dst, peer_k[from], bytes, cudaMemcpyDeviceToDevice, st->s_ring));
+    FA_CUDA_TRY(cudaMemcpyAsync(dst + L.shard_bytes, peer_v[from], bytes, cudaMemcpyDeviceToDevice, st->s_ring));
+    FA_CUDA_TRY(cudaEventRecord(st->ev_ring_recv[x], st->s_ring));
+    return FA_OK;
+  };
+  FA_CUDA_TRY(cudaEventRecord(st->ev_ring_ready, s));  // the workspace is free where the caller's stream stands now
+  FA_CUDA_TRY(cudaStreamWaitEvent(st->s_ring, st->ev_ring_ready, 0));
+  for (int x = 1; x <= depth && x < world; ++x)
+    if ((rc = fetch(x)) != FA_OK) return rc;
+  if ((rc = fa_forward_partial(Q, K, V, o_acc, m, l, B, H, n, n, D, scale, 1, 0, nullptr, stream)) != FA_OK) return rc;
+  for (int x = 1; x < world; ++x) {
+    char* const src = kbuf((x - 1) % depth);
+    FA_CUDA_TRY(cudaStreamWaitEvent(s, st->ev_ring_recv[x], 0));
+    if ((rc = fa_forward_partial(Q, src, src + L.shard_bytes, o_acc, m, l, B, H, n, n, D, scale, 0, x == world - 1 ? 1 : 0,
+                                 O, stream)) != FA_OK)
+      return rc;
+    if (x + depth < world) {
+      FA_CUDA_TRY(cudaEventRecord(st->ev_ring_step[x], s));
+      FA_CUDA_TRY(cudaStreamWaitEvent(st->s_ring, st->ev_ring_step[x], 0));
+      if ((rc = fetch(x + depth)) != FA_OK) return rc;
+    }
+  }
+  return FA_OK;
+}
+
 int fa_forward_cross(const void* Q, const void* K, const void* V, float* O, int B, int H, int Nq, int Nkv, int D,
                      float scale, void* stream) {
   if (D == 16) {

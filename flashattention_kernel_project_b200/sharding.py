@@ -69,10 +69,15 @@ class RingWorkspace:
             raise RuntimeError("allocator returned memory that is not 256-byte aligned")
 
 
-def ring_forward(q, k, v, scale=None, group=None, out=None, workspace=None, depth=0, stream=None):
-    """Context-parallel attention over the ranks of `group` through the C ABI `fa_ring_forward` (one call per
-    rank, same shapes everywhere).  q, k, v: this rank's [B, H, N/P, D] fp16 shards; returns this rank's rows of O.
-    Nothing is synchronised on the host: the call only enqueues on `stream` and on the library's exchange stream."""
+def ring_forward(q, k, v, scale=None, group=None, out=None, workspace=None, depth=0, stream=None, peers=None):
+    """Context-parallel attention over the ranks of `group` through the C ABI (one call per rank, same shapes
+    everywhere).  q, k, v: this rank's [B, H, N/P, D] fp16 shards; returns this rank's rows of O.
+    Nothing is synchronised on the host: the call only enqueues on `stream` and on the library's exchange stream.
+
+    peers=None: `fa_ring_forward`, the exchange is grouped ncclSend / ncclRecv on the group's communicator.
+    peers=PeerShards(k, v): `fa_ring_forward_pull`, every shard is pulled from its owner by this GPU's copy engines
+    through the peer mappings (no SMs, no rank-to-rank synchronisation inside the call; the caller keeps K / V
+    unchanged between the barriers PeerShards places at construction and close())."""
     import ctypes
     from ._lib import check, load_library
     if not (q.is_cuda and k.is_cuda and v.is_cuda):
@@ -97,8 +102,20 @@ def ring_forward(q, k, v, scale=None, group=None, out=None, workspace=None, dept
         workspace = RingWorkspace(q.shape, world, q.device, depth)
     elif workspace.shape != (B, H, n, D) or workspace.world != world or workspace.buffer.device != q.device:
         raise ValueError("workspace was made for another shape, world size or device")
-    comm = _nccl_comm_ptr(group, q.device) if world > 1 else None
     s = torch.cuda.current_stream(q.device) if stream is None else stream
+    if peers is not None and world > 1:
+        if peers.world != world or peers.rank != rank:
+            raise ValueError("peers was made for another group")
+        pk = (ctypes.c_void_p * world)(*[ctypes.c_void_p(peers.owner(r)[0].data_ptr()) for r in range(world)])
+        pv = (ctypes.c_void_p * world)(*[ctypes.c_void_p(peers.owner(r)[1].data_ptr()) for r in range(world)])
+        with torch.cuda.device(q.device):
+            check(load_library().fa_ring_forward_pull(
+                ctypes.c_void_p(q.data_ptr()), ctypes.c_void_p(k.data_ptr()), ctypes.c_void_p(v.data_ptr()),
+                ctypes.c_void_p(out.data_ptr()), B, H, n, D, float(scale), rank, world, pk, pv,
+                ctypes.c_void_p(workspace.buffer.data_ptr()), ctypes.c_size_t(workspace.nbytes),
+                ctypes.c_void_p(s.cuda_stream)), "fa_ring_forward_pull")
+        return out
+    comm = _nccl_comm_ptr(group, q.device) if world > 1 else None
     with torch.cuda.device(q.device):
         check(load_library().fa_ring_forward(
             ctypes.c_void_p(q.data_ptr()), ctypes.c_void_p(k.data_ptr()), ctypes.c_void_p(v.data_ptr()),
@@ -192,6 +209,13 @@ class PeerShards:
         self._shards = []
         for r, ((fk, ak), (fv, av)) in enumerate(handles):
             self._shards.append((k, v) if r == self.rank else (fk(*ak), fv(*av)))
+        # direct access from this GPU to every owner's memory: without it the driver stages a cudaMemcpyAsync between
+        # two devices through host memory (round 1 measured 14 GB/s on exactly that path)
+        from ._lib import check, load_library
+        with torch.cuda.device(k.device):
+            for r, (pk, _) in enumerate(self._shards):
+                if r != self.rank:
+                    check(load_library().fa_enable_peer_access(pk.device.index), "fa_enable_peer_access")
         # ... and no rank starts reading before every rank has mapped every shard (mirrors close())
         dist.barrier(group=group)
 

@@ -122,6 +122,24 @@ int fa_ring_forward(const void* Q, const void* K, const void* V, void* O, int B,
                     int rank, int world, void* nccl_comm, void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * The same ring with the exchange done by the COPY ENGINES instead of NCCL kernels: peer_k[r] / peer_v[r] are
+ * addresses, valid in THIS process, of rank r's K / V shard (CUDA IPC mappings of the other processes' buffers, or
+ * plain pointers when one process drives several GPUs; entry `rank` is ignored).  Each step's shard is pulled from its
+ * owner over NVLink / NVSwitch with cudaMemcpyAsync on an internal stream of the calling GPU: no SM is taken from
+ * the attention kernel (at 8 ranks NCCL's send/recv kernels run 4 channels per peer, ~70 GB/s, and hold SMs that a
+ * 227 KB attention CTA cannot share), and no rank waits for another inside the call.  Arithmetic, visiting order and
+ * workspace are those of fa_ring_forward: the two return bit-identical results.
+ * The caller orders the ranks around the call: every rank's K / V must be complete before any rank starts, and
+ * unmodified until every rank's call has finished (one barrier on each side).  fa_enable_peer_access(d) enables
+ * direct access from the current device to device d (once per pair; without it the driver stages peer copies
+ * through host memory).
+ */
+int fa_enable_peer_access(int peer_device);
+int fa_ring_forward_pull(const void* Q, const void* K, const void* V, void* O, int B, int H, int n, int D, float scale,
+                         int rank, int world, const void* const* peer_k, const void* const* peer_v, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
+/*
  * C = ReLU(A*B + bias[col]) + residual   (epilogue order: bias -> ReLU -> residual).
  *   A fp16 [M,K] row-major; Bm fp16 [K,N] row-major (NOT transposed); bias fp32 [N] or NULL;
  *   residual fp32 [M,N] or NULL; C fp32 [M,N].  K % 8 == 0 and N % 8 == 0 (16-byte row pitch).

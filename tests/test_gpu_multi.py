@@ -55,6 +55,14 @@ def _worker(rank, world, port, mode, q, k, v, scale, out_path):
                 tight = fa.ring_forward(qs, ks, vs, scale, depth=1)
                 torch.cuda.synchronize()
                 assert torch.equal(native, out) and torch.equal(again, out) and torch.equal(tight, out)
+                # the same loop with the exchange done by this GPU's copy engines through peer mappings
+                # (fa_ring_forward_pull): same arithmetic in the same order
+                peers = fa.PeerShards(ks, vs)
+                pulled = fa.ring_forward(qs, ks, vs, scale, workspace=ws, peers=peers)
+                pulled_tight = fa.ring_forward(qs, ks, vs, scale, depth=1, peers=peers)
+                torch.cuda.synchronize()
+                peers.close()
+                assert torch.equal(pulled, out) and torch.equal(pulled_tight, out)
                 out = native
             if mode == "pull":
                 # the same ring with every K/V shard peer-mapped and pulled from its owner by the copy engines:
