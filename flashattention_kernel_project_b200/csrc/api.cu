@@ -242,6 +242,12 @@ struct FaCall {
   int B, H, Nq, Nkv, D;
   float scale;
   int mode, is_first, is_last;
+  // fused ring exchange (fa_ring_forward_pull): next step's K / V shard, peer source -> local destination
+  const void* pf_src_k = nullptr;
+  const void* pf_src_v = nullptr;
+  void* pf_dst_k = nullptr;
+  void* pf_dst_v = nullptr;
+  size_t pf_bytes = 0;
 };
 
 // How the grid is cut (fa_fwd.cuh, FaSegment).  The kernel can cut the items of a partial last wave along K/V into
@@ -359,6 +365,11 @@ int launch_fa(DeviceState* st, const FaCall& c, cudaStream_t stream) {
   p.tail_ctas = plan.tail_ctas;
   p.ws = nullptr;
   p.ws_count = nullptr;
+  p.pf_src[0] = static_cast<const uint4*>(c.pf_src_k);
+  p.pf_src[1] = static_cast<const uint4*>(c.pf_src_v);
+  p.pf_dst[0] = static_cast<uint4*>(c.pf_dst_k);
+  p.pf_dst[1] = static_cast<uint4*>(c.pf_dst_v);
+  p.pf_words = c.pf_bytes / 16;
   void* ws = nullptr;
   if (plan.tail_ctas > 0) {
     // [counters, padded to 256 B][tail_ctas * 2 slots of (D + 2) * 256 floats]
@@ -850,39 +861,37 @@ int fa_ring_forward_pull(const void* Q, const void* K, const void* V, void* O, i
   float* const o_acc = reinterpret_cast<float*>(ws + L.state_o);
   float* const m = reinterpret_cast<float*>(ws + L.state_m);
   float* const l = reinterpret_cast<float*>(ws + L.state_l);
-  const cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (world == 1) return fa_forward_partial(Q, K, V, o_acc, m, l, B, H, n, n, D, scale, 1, 1, O, stream);
-  if ((rc = ring_init(st)) != FA_OK) return rc;
-  std::lock_guard<std::mutex> ring_lock(st->host_mu);
-  const size_t bytes = static_cast<size_t>(B) * H * n * D * 2;
-  const int depth = L.depth;
+  const size_t bytes = static_cast<size_t>(B) * H * n * D * 2;  // a multiple of 16: D is 64 or 128
+  const int depth = L.depth < 2 ? L.depth : 2;  // the step after next reuses the buffer this step reads
+  if (world > 2 && depth < 2) return FA_ERR_BAD_ARGUMENT;
   auto kbuf = [&](int slot) { return ws + L.kv + static_cast<size_t>(slot) * 2 * L.shard_bytes; };
-  // Fetch x: the shard of rank - x, copied by THIS GPU's copy engines straight out of its owner's memory (peer
-  // mapping over NVLink / NVSwitch): no SM is taken from the attention kernel, no rank synchronises with another.
-  auto fetch = [&](int x) -> int {
-    const int from = (rank - x + world) % world;
-    char* const dst = kbuf((x - 1) % depth);
-    FA_CUDA_TRY(cudaMemcpyAsync(dst, peer_k[from], bytes, cudaMemcpyDeviceToDevice, st->s_ring));
-    FA_CUDA_TRY(cudaMemcpyAsync(dst + L.shard_bytes, peer_v[from], bytes, cudaMemcpyDeviceToDevice, st->s_ring));
-    FA_CUDA_TRY(cudaEventRecord(st->ev_ring_recv[x], st->s_ring));
-    return FA_OK;
-  };
-  FA_CUDA_TRY(cudaEventRecord(st->ev_ring_ready, s));  // the workspace is free where the caller's stream stands now
-  FA_CUDA_TRY(cudaStreamWaitEvent(st->s_ring, st->ev_ring_ready, 0));
-  for (int x = 1; x <= depth && x < world; ++x)
-    if ((rc = fetch(x)) != FA_OK) return rc;
-  if ((rc = fa_forward_partial(Q, K, V, o_acc, m, l, B, H, n, n, D, scale, 1, 0, nullptr, stream)) != FA_OK) return rc;
-  for (int x = 1; x < world; ++x) {
-    char* const src = kbuf((x - 1) % depth);
-    FA_CUDA_TRY(cudaStreamWaitEvent(s, st->ev_ring_recv[x], 0));
-    if ((rc = fa_forward_partial(Q, src, src + L.shard_bytes, o_acc, m, l, B, H, n, n, D, scale, 0, x == world - 1 ? 1 : 0,
-                                 O, stream)) != FA_OK)
-      return rc;
-    if (x + depth < world) {
-      FA_CUDA_TRY(cudaEventRecord(st->ev_ring_step[x], s));
-      FA_CUDA_TRY(cudaStreamWaitEvent(st->s_ring, st->ev_ring_step[x], 0));
-      if ((rc = fetch(x + depth)) != FA_OK) return rc;
+  // Step x attends to the shard of rank - x (step 0: the local one) and, with the two spare warps of every CTA,
+  // pulls the shard of rank - (x + 1) out of its owner's memory into the other buffer.  One launch per step, all
+  // on the caller's stream; nothing else is enqueued.
+  for (int x = 0; x < world; ++x) {
+    FaCall c{};
+    c.Q = Q;
+    c.K = x == 0 ? K : kbuf((x - 1) % depth);
+    c.V = x == 0 ? V : kbuf((x - 1) % depth) + L.shard_bytes;
+    c.O16 = x == world - 1 ? O : nullptr;
+    c.O32 = o_acc;
+    c.m = m;
+    c.l = l;
+    c.B = B; c.H = H; c.Nq = n; c.Nkv = n; c.D = D;
+    c.scale = scale;
+    c.mode = FA_MODE_STATE;
+    c.is_first = x == 0 ? 1 : 0;
+    c.is_last = x == world - 1 ? 1 : 0;
+    if (x + 1 < world) {
+      const int from = (rank - (x + 1) + world) % world;
+      c.pf_src_k = peer_k[from];
+      c.pf_src_v = peer_v[from];
+      c.pf_dst_k = kbuf(x % depth);
+      c.pf_dst_v = kbuf(x % depth) + L.shard_bytes;
+      c.pf_bytes = bytes;
     }
+    if ((rc = run_fa(c, stream)) != FA_OK) return rc;
   }
   return FA_OK;
 }

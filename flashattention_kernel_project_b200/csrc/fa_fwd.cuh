@@ -52,6 +52,12 @@ struct FaParams {
   int tail_ctas;
   float* ws;               // tail_ctas * 2 slots of (D + 2) * 256 floats: un-normalised O, row max, row sum
   unsigned int* ws_count;  // [tail_items] arrival counters, zero before the launch
+  // Ring attention, fused exchange: while this launch computes on one K/V shard, the two otherwise idle warps of
+  // every CTA copy the NEXT step's shard out of its owner's memory (a peer mapping: the loads travel over NVLink /
+  // NVSwitch) into a local buffer.  [0] = K, [1] = V; pf_words 16-byte words each, 0 = nothing to fetch.
+  const uint4* pf_src[2];
+  uint4* pf_dst[2];
+  unsigned long long pf_words;
   DebugChannel dbg;
 #ifdef FA_TRACE
   long long* trace;  // [6 roles][64 iterations][8 points]
@@ -833,7 +839,31 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
       }
     }
   } else {
+    // ============================ warps 14 / 15: peer prefetch =========================
+    // Idle in a plain attention call (they only hold registers for the softmax warps).  In a ring step they are the
+    // exchange: warp 14 pulls K, warp 15 pulls V of the next step, each CTA its 1 / gridDim.x slice of the shard --
+    // 134 MB per step of BASELINE config 4 on 8 GPUs is 64 KB per warp, a few loads in flight per lane.  No SM is
+    // taken from the attention kernel (NCCL's send/recv CTAs cannot share an SM with a 227 KB CTA), no second
+    // stream, no events: the next step's launch follows this one in stream order and finds its shard in place.
     setmaxnreg_dec<48>();
+    if (p.pf_words != 0ull) {
+      const int lane = threadIdx.x & 31;
+      const uint4* const src = p.pf_src[warp - 14];
+      uint4* const dst = p.pf_dst[warp - 14];
+      const unsigned long long per = (p.pf_words + gridDim.x - 1) / gridDim.x;
+      const unsigned long long w0 = per * blockIdx.x;
+      const unsigned long long w1 = w0 + per < p.pf_words ? w0 + per : p.pf_words;
+      constexpr int kInFlight = 4;  // 16-byte loads in flight per lane: 296 warps x 2 KB cover ~2 us of NVLink latency at 300 GB/s
+      for (unsigned long long w = w0 + lane; w < w1; w += 32ull * kInFlight) {
+        uint4 r[kInFlight];
+#pragma unroll
+        for (int u = 0; u < kInFlight; ++u)
+          if (w + 32ull * u < w1) r[u] = __ldcv(src + w + 32ull * u);  // .cv: never a stale line of an earlier call
+#pragma unroll
+        for (int u = 0; u < kInFlight; ++u)
+          if (w + 32ull * u < w1) __stcs(dst + w + 32ull * u, r[u]);
+      }
+    }
   }
 
   // ---------------------------------- teardown ----------------------------------------

@@ -227,6 +227,11 @@ class PeerShards:
         torch.cuda.synchronize()
         dist.barrier(group=self.group)
         self._shards = []
+        # release the consumer side of the IPC mappings now, and tell every owner before it may free its shard
+        import gc
+        gc.collect()
+        torch.cuda.ipc_collect()
+        dist.barrier(group=self.group)
 
 
 def ring_attention_pull(q, peers, scale, step_fn=None, copy_stream=None):
