@@ -23,6 +23,9 @@ SIGNATURES = {
     "fa_ring_workspace_bytes": (ctypes.c_size_t, [c_int] * 6),
     "fa_ring_forward": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_float, c_int, c_int, c_void_p, c_void_p, ctypes.c_size_t, c_void_p]),
     "fa_enable_peer_access": (c_int, [c_int]),
+    "fa_ipc_export": (c_int, [c_void_p, ctypes.POINTER(ctypes.c_ubyte), ctypes.POINTER(ctypes.c_ulonglong)]),
+    "fa_ipc_open": (c_int, [ctypes.POINTER(ctypes.c_ubyte), ctypes.POINTER(c_void_p)]),
+    "fa_ipc_close": (c_int, [c_void_p]),
     "fa_ring_forward_pull": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_float, c_int, c_int, ctypes.POINTER(c_void_p),
                                      ctypes.POINTER(c_void_p), c_void_p, ctypes.c_size_t, c_void_p]),
     "gemm_fused_epilogue": (c_int, [c_void_p] * 5 + [c_int] * 3 + [c_void_p]),

@@ -819,6 +819,55 @@ int fa_ring_forward(const void* Q, const void* K, const void* V, void* O, int B,
   return FA_OK;
 }
 
+int fa_ipc_export(const void* ptr, unsigned char* handle, unsigned long long* offset) {
+  if (ptr == nullptr || handle == nullptr || offset == nullptr) return FA_ERR_NULL_POINTER;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the header promises 64-byte handles");
+  using RangeFn = CUresult (*)(CUdeviceptr*, size_t*, CUdeviceptr);
+  static RangeFn range_fn = [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      fn = nullptr;
+    return reinterpret_cast<RangeFn>(fn);
+  }();
+  if (range_fn == nullptr) return FA_ERR_DRIVER_ENTRY;
+  CUdeviceptr base = 0;
+  size_t size = 0;
+  if (range_fn(&base, &size, reinterpret_cast<CUdeviceptr>(ptr)) != CUDA_SUCCESS) return FA_ERR_BAD_ARGUMENT;
+  cudaIpcMemHandle_t h;
+  const cudaError_t e = cudaIpcGetMemHandle(&h, reinterpret_cast<void*>(base));  // the handle names the allocation
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return static_cast<int>(e);
+  }
+  std::memcpy(handle, &h, sizeof(h));
+  *offset = static_cast<unsigned long long>(reinterpret_cast<CUdeviceptr>(ptr) - base);
+  return FA_OK;
+}
+
+int fa_ipc_open(const unsigned char* handle, void** base) {
+  if (handle == nullptr || base == nullptr) return FA_ERR_NULL_POINTER;
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle, sizeof(h));
+  const cudaError_t e = cudaIpcOpenMemHandle(base, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return static_cast<int>(e);
+  }
+  return FA_OK;
+}
+
+int fa_ipc_close(void* base) {
+  if (base == nullptr) return FA_ERR_NULL_POINTER;
+  const cudaError_t e = cudaIpcCloseMemHandle(base);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return static_cast<int>(e);
+  }
+  return FA_OK;
+}
+
 int fa_enable_peer_access(int peer_device) {
   int dev = -1;
   if (cudaGetDevice(&dev) != cudaSuccess) {

@@ -11,12 +11,11 @@
   `ring_forward` is the product path: the whole loop runs inside the library (C ABI `fa_ring_forward`: the
   partial-attention launches and grouped ncclSend / ncclRecv on a high-priority stream, tied together with events
   from C++; every rank sends its own read-only shard straight to the rank that needs it next, so all exchanges
-  are in flight from the start and none waits for an earlier one).  The two Python-orchestrated variants below
-  are kept as the independent implementations it is tested against: `ring_attention` passes shards
-  rank -> rank+1 with NCCL send/recv; `ring_attention_pull` maps every rank's K/V shard into every process (CUDA IPC over NVLink /
-  NVSwitch) and each rank fetches the shard it needs next straight from its owner with the copy engines --
-  K/V are read-only, so nothing has to be passed along and the ranks do not synchronise inside the loop.
-  Bit-identical results; kept as the stepping stone to reading peer K/V tiles from inside the kernel.
+  are in flight from the start and none waits for an earlier one; or, with `peers=`, `fa_ring_forward_pull`: no
+  NCCL at all, the attention kernel's spare warps load the next shard from its owner's memory over NVLink).
+  The Python-orchestrated `ring_attention` below is kept as the independent implementation it is tested against:
+  it passes shards rank -> rank+1 with NCCL send/recv.  (Round 1's copy-engine variant is gone: cudaMemcpyAsync
+  from a peer mapping runs at 25 GB/s on this platform.)
 
 Only the ring communicates; `torch.distributed` is plumbing (NCCL on GPUs, gloo in the CPU tests, which
 exercise the schedule with an injected step function).
@@ -75,9 +74,10 @@ def ring_forward(q, k, v, scale=None, group=None, out=None, workspace=None, dept
     Nothing is synchronised on the host: the call only enqueues on `stream` and on the library's exchange stream.
 
     peers=None: `fa_ring_forward`, the exchange is grouped ncclSend / ncclRecv on the group's communicator.
-    peers=PeerShards(k, v): `fa_ring_forward_pull`, every shard is pulled from its owner by this GPU's copy engines
-    through the peer mappings (no SMs, no rank-to-rank synchronisation inside the call; the caller keeps K / V
-    unchanged between the barriers PeerShards places at construction and close())."""
+    peers=PeerShards(k, v): `fa_ring_forward_pull`, the exchange is fused into the attention kernel -- the two spare
+    warps of every CTA load the next step's shard from its owner through the peer mappings (no extra launches, no
+    SMs taken, no rank-to-rank synchronisation inside the call; the caller keeps K / V unchanged between the barriers
+    PeerShards places at construction and close())."""
     import ctypes
     from ._lib import check, load_library
     if not (q.is_cuda and k.is_cuda and v.is_cuda):
@@ -106,8 +106,8 @@ def ring_forward(q, k, v, scale=None, group=None, out=None, workspace=None, dept
     if peers is not None and world > 1:
         if peers.world != world or peers.rank != rank:
             raise ValueError("peers was made for another group")
-        pk = (ctypes.c_void_p * world)(*[ctypes.c_void_p(peers.owner(r)[0].data_ptr()) for r in range(world)])
-        pv = (ctypes.c_void_p * world)(*[ctypes.c_void_p(peers.owner(r)[1].data_ptr()) for r in range(world)])
+        pk = (ctypes.c_void_p * world)(*[ctypes.c_void_p(peers.ptrs(r)[0]) for r in range(world)])
+        pv = (ctypes.c_void_p * world)(*[ctypes.c_void_p(peers.ptrs(r)[1]) for r in range(world)])
         with torch.cuda.device(q.device):
             check(load_library().fa_ring_forward_pull(
                 ctypes.c_void_p(q.data_ptr()), ctypes.c_void_p(k.data_ptr()), ctypes.c_void_p(v.data_ptr()),
@@ -188,88 +188,66 @@ def ring_attention(q, k, v, scale, group=None, step_fn=None, comm_stream=None):
 
 
 class PeerShards:
-    """Every rank's K/V shard, mapped into this process (CUDA IPC; peer access over NVLink / NVSwitch).
+    """Every rank's K/V shard, mapped into this process over NVLink / NVSwitch (CUDA IPC through the library's
+    fa_ipc_* entry points, opened in THIS GPU's context so that its kernels can load from them directly).
 
-    Collective over `group`: all ranks construct it together with their own [B, H, N/P, D] fp16 shards, which
-    must stay allocated and unmodified until `close()` (also collective).  `owner(r)` returns (k, v) tensors
-    that live on rank r's GPU; reading them from a kernel or a copy on this rank's GPU goes over NVLink."""
+    Collective over `group`: all ranks construct it together with their own [B, H, N/P, D] fp16 shards, which must
+    stay allocated and unmodified until `close()` (also collective).  `ptrs(r)` returns the (K, V) addresses of rank
+    r's shard as seen from this process (its own tensors' addresses for r == rank)."""
 
     def __init__(self, k, v, group=None):
-        from torch.multiprocessing.reductions import reduce_tensor
+        import ctypes
+        from ._lib import check, load_library
         if not (k.is_cuda and v.is_cuda and k.is_contiguous() and v.is_contiguous()):
             raise ValueError("K and V shards must be contiguous CUDA tensors")
+        lib = load_library()
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self._local = (k, v)
-        handles = [None] * self.world
+        self._device = k.device
+
+        def export(t):
+            handle = (ctypes.c_ubyte * 64)()
+            offset = ctypes.c_ulonglong(0)
+            check(lib.fa_ipc_export(ctypes.c_void_p(t.data_ptr()), handle, ctypes.byref(offset)), "fa_ipc_export")
+            return bytes(handle), int(offset.value)
         # whatever produced k and v on this rank has finished before any peer can see the handles ...
         torch.cuda.synchronize(k.device)
-        dist.all_gather_object(handles, (reduce_tensor(k), reduce_tensor(v)), group=group)
-        self._shards = []
-        for r, ((fk, ak), (fv, av)) in enumerate(handles):
-            self._shards.append((k, v) if r == self.rank else (fk(*ak), fv(*av)))
-        # direct access from this GPU to every owner's memory: without it the driver stages a cudaMemcpyAsync between
-        # two devices through host memory (round 1 measured 14 GB/s on exactly that path)
-        from ._lib import check, load_library
         with torch.cuda.device(k.device):
-            for r, (pk, _) in enumerate(self._shards):
-                if r != self.rank:
-                    check(load_library().fa_enable_peer_access(pk.device.index), "fa_enable_peer_access")
+            mine = (export(k), export(v))
+        table = [None] * self.world
+        dist.all_gather_object(table, mine, group=group)
+        self._bases = {}  # handle bytes -> mapped base address (one mapping per allocation and process)
+        self._ptrs = []
+        with torch.cuda.device(k.device):
+            for r, entry in enumerate(table):
+                if r == self.rank:
+                    self._ptrs.append((k.data_ptr(), v.data_ptr()))
+                    continue
+                pair = []
+                for handle, offset in entry:
+                    if handle not in self._bases:
+                        base = ctypes.c_void_p()
+                        buf = (ctypes.c_ubyte * 64).from_buffer_copy(handle)
+                        check(lib.fa_ipc_open(buf, ctypes.byref(base)), "fa_ipc_open")
+                        self._bases[handle] = int(base.value)
+                    pair.append(self._bases[handle] + offset)
+                self._ptrs.append(tuple(pair))
         # ... and no rank starts reading before every rank has mapped every shard (mirrors close())
         dist.barrier(group=group)
 
-    def owner(self, r):
-        return self._shards[r]
+    def ptrs(self, r):
+        return self._ptrs[r]
 
     def close(self):
         """No rank may free or overwrite its shard while another still reads it."""
-        torch.cuda.synchronize()
+        import ctypes
+        from ._lib import check, load_library
+        torch.cuda.synchronize(self._device)
         dist.barrier(group=self.group)
-        self._shards = []
-        # release the consumer side of the IPC mappings now, and tell every owner before it may free its shard
-        import gc
-        gc.collect()
-        torch.cuda.ipc_collect()
+        with torch.cuda.device(self._device):
+            for base in self._bases.values():
+                check(load_library().fa_ipc_close(ctypes.c_void_p(base)), "fa_ipc_close")
+        self._bases, self._ptrs = {}, []
         dist.barrier(group=self.group)
-
-
-def ring_attention_pull(q, peers, scale, step_fn=None, copy_stream=None):
-    """Context-parallel attention where each rank pulls the K/V shard of step s+1 from its OWNER while step s
-    computes (`peers`: a PeerShards made from this rank's k, v).  Same arithmetic and the same visiting order as
-    `ring_attention` (owner (rank - s) mod P at step s), so the two return bit-identical results.
-    The pulls are peer-to-peer copies on the copy engines: the attention kernel keeps every SM."""
-    if step_fn is None:
-        from .ops import fa_forward_partial as step_fn
-    world, rank = peers.world, peers.rank
-    k, v = peers.owner(rank)
-    B, H, Nq, D = q.shape
-    o_acc = torch.empty((B, H, Nq, D), dtype=torch.float32, device=q.device)
-    m = torch.empty((B, H, Nq), dtype=torch.float32, device=q.device)
-    l = torch.empty((B, H, Nq), dtype=torch.float32, device=q.device)
-    out = torch.empty_like(q)
-    compute_stream = torch.cuda.current_stream(q.device)
-    if copy_stream is None:
-        copy_stream = torch.cuda.Stream(device=q.device)
-    bufs = [(torch.empty_like(k), torch.empty_like(v)) for _ in range(min(2, world - 1))]
-    cur_k, cur_v = k, v
-    order = ring_schedule(world, rank)
-    for s in range(world):
-        nxt = None
-        if s + 1 < world:
-            pk, pv = peers.owner(order[s + 1])
-            nxt = bufs[s & 1]
-            copy_stream.wait_stream(compute_stream)  # the buffer was last read by the kernel of step s - 1
-            # Tensor.copy_ enqueues a cross-device transfer on the OWNER's GPU (this process's context there) and
-            # ties it to copy_stream with events.  Measured on 8 x B200 (config 4): 10.5 ms against 9.2 ms for the
-            # NCCL exchange -- the foreign context is time-sliced against the owner's own attention kernel; the same
-            # transfer issued as cudaMemcpyAsync on THIS device's stream (a true pull) ran at ~14 GB/s (72 ms).
-            # NCCL send/recv on a high-priority stream therefore stays the default exchange.
-            with torch.cuda.stream(copy_stream):
-                nxt[0].copy_(pk, non_blocking=True)
-                nxt[1].copy_(pv, non_blocking=True)
-        step_fn(q, cur_k, cur_v, o_acc, m, l, scale, s == 0, s == world - 1, out)
-        if nxt is not None:
-            compute_stream.wait_stream(copy_stream)
-            cur_k, cur_v = nxt
-    return out

@@ -122,19 +122,40 @@ int fa_ring_forward(const void* Q, const void* K, const void* V, void* O, int B,
                     int rank, int world, void* nccl_comm, void* workspace, size_t workspace_bytes, void* stream);
 
 /*
- * The same ring with the exchange done by the COPY ENGINES instead of NCCL kernels: peer_k[r] / peer_v[r] are
- * addresses, valid in THIS process, of rank r's K / V shard (CUDA IPC mappings of the other processes' buffers, or
- * plain pointers when one process drives several GPUs; entry `rank` is ignored).  Each step's shard is pulled from its
- * owner over NVLink / NVSwitch with cudaMemcpyAsync on an internal stream of the calling GPU: no SM is taken from
- * the attention kernel (at 8 ranks NCCL's send/recv kernels run 4 channels per peer, ~70 GB/s, and hold SMs that a
- * 227 KB attention CTA cannot share), and no rank waits for another inside the call.  Arithmetic, visiting order and
- * workspace are those of fa_ring_forward: the two return bit-identical results.
+ * The same ring with the exchange FUSED INTO THE ATTENTION KERNEL: peer_k[r] / peer_v[r] are addresses, valid in
+ * THIS process, of rank r's K / V shard (peer mappings made with fa_ipc_open, or plain pointers when one process
+ * drives several GPUs; entry `rank` is ignored).  The launch of step x attends to the shard of rank - x and, with the
+ * two warps of every CTA that are otherwise idle, loads the shard of rank - (x + 1) straight out of its owner's
+ * memory over NVLink / NVSwitch into the other of two local buffers (ld.global.cv on the peer mapping, 16 bytes per
+ * lane, every CTA its 1 / grid slice).  One launch per step on the caller's stream and nothing else: no NCCL, no
+ * second stream, no events, no SM taken from the attention kernel (NCCL's send/recv CTAs cannot share an SM with a
+ * 227 KB attention CTA, and at 8 ranks its point-to-point exchange ran at ~70 GB/s per peer: 14.3 ms for config 4
+ * against 7.7 ms of compute), and no rank waits for another inside the call.  The copy engines are not an
+ * alternative on this platform: cudaMemcpyAsync from a peer mapping measured 25 GB/s.
+ * Arithmetic, visiting order and workspace layout are those of fa_ring_forward (two receive buffers are enough):
+ * the two return bit-identical results.
  * The caller orders the ranks around the call: every rank's K / V must be complete before any rank starts, and
  * unmodified until every rank's call has finished (one barrier on each side).  fa_enable_peer_access(d) enables
  * direct access from the current device to device d (once per pair; without it the driver stages peer copies
  * through host memory).
  */
 int fa_enable_peer_access(int peer_device);
+/*
+ * Peer mappings between the one-process-per-GPU ranks (thin wrappers of CUDA IPC; no framework needed):
+ *   fa_ipc_export(ptr, handle, &offset)  in the OWNER process: the 64-byte handle of the allocation that contains
+ *                                        `ptr` and ptr's byte offset inside it (send both to the other ranks);
+ *   fa_ipc_open(handle, &base)           in a CONSUMER process, with the consuming GPU current: maps the allocation
+ *                                        with peer access over NVLink enabled; the shard is at base + offset.  Open a
+ *                                        given handle once per process and share the mapping (K and V of one rank
+ *                                        often live in one allocation);
+ *   fa_ipc_close(base)                   unmaps; the owner may free the allocation afterwards.
+ * The mapping must be opened in the CONSUMER's context: a mapping opened on the owner's device index (what a
+ * framework's tensor sharing does) can be copied from by the driver (staged, 25 GB/s measured) but faults when a
+ * kernel of another GPU loads from it.
+ */
+int fa_ipc_export(const void* ptr, unsigned char* handle /* [64] */, unsigned long long* offset);
+int fa_ipc_open(const unsigned char* handle /* [64] */, void** base);
+int fa_ipc_close(void* base);
 int fa_ring_forward_pull(const void* Q, const void* K, const void* V, void* O, int B, int H, int n, int D, float scale,
                          int rank, int world, const void* const* peer_k, const void* const* peer_v, void* workspace,
                          size_t workspace_bytes, void* stream);

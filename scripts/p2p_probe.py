@@ -42,12 +42,12 @@ ms = e0.elapsed_time(e1) / 5
 if rank == 0:
     print(f"NCCL send/recv 256 MiB each way, alone: {ms:.3f} ms -> {x.numel() / ms / 1e6:.0f} GB/s per direction", flush=True)
 peers = fa.PeerShards(x, x)
-src = peers.owner((rank - 1) % world)[0]
+src_ptr = peers.ptrs((rank - 1) % world)[0]
 side = torch.cuda.Stream(device=dev)
 
 
 def pull(stream):
-    rc = cudart.cudaMemcpyAsync(y.data_ptr(), src.data_ptr(), x.numel(), 3, stream.cuda_stream)
+    rc = cudart.cudaMemcpyAsync(y.data_ptr(), src_ptr, x.numel(), 3, stream.cuda_stream)
     assert rc == 0, rc
 
 

@@ -1,7 +1,8 @@
 """Multi-GPU GPU tests (skipped on a single-GPU box; run with `gpurun --gpus 2`): (b,h) sharding with no
 collective, and the ring / context-parallel path -- the product entry fa_ring_forward (C++ loop, NCCL exchange), and
-the two Python-orchestrated rings it is checked against: K/V passed along with NCCL send/recv, and pulled from their
-owners through CUDA IPC peer mappings.  The driver's 1-GPU box skips these; the ring's parity at 2 / 4 / 8 GPUs is
+its fused form fa_ring_forward_pull (the attention kernel's spare warps load the next shard from its owner's memory
+through CUDA IPC peer mappings), and the Python-orchestrated ring they are checked against (K/V passed along with NCCL
+send/recv).  The driver's 1-GPU box skips these; the ring's parity at 2 / 4 / 8 GPUs is
 also checked inside `bench.py --gpus N` (extras.ring_cfg4.parity), which the driver does run."""
 import os
 import socket
@@ -55,8 +56,8 @@ def _worker(rank, world, port, mode, q, k, v, scale, out_path):
                 tight = fa.ring_forward(qs, ks, vs, scale, depth=1)
                 torch.cuda.synchronize()
                 assert torch.equal(native, out) and torch.equal(again, out) and torch.equal(tight, out)
-                # the same loop with the exchange done by this GPU's copy engines through peer mappings
-                # (fa_ring_forward_pull): same arithmetic in the same order
+                # the same loop with the exchange fused into the attention kernel (fa_ring_forward_pull): its spare
+                # warps load the next shard from the owner's memory through peer mappings; same arithmetic, same order
                 peers = fa.PeerShards(ks, vs)
                 pulled = fa.ring_forward(qs, ks, vs, scale, workspace=ws, peers=peers)
                 pulled_tight = fa.ring_forward(qs, ks, vs, scale, depth=1, peers=peers)
@@ -64,15 +65,6 @@ def _worker(rank, world, port, mode, q, k, v, scale, out_path):
                 peers.close()
                 assert torch.equal(pulled, out) and torch.equal(pulled_tight, out)
                 out = native
-            if mode == "pull":
-                # the same ring with every K/V shard peer-mapped and pulled from its owner by the copy engines:
-                # same visiting order, same kernel calls -> bit-identical to the NCCL exchange
-                peers = fa.PeerShards(ks, vs)
-                pulled = fa.ring_attention_pull(qs, peers, scale)
-                again = fa.ring_attention_pull(qs, peers, scale)  # buffers and mappings are reusable
-                peers.close()
-                assert torch.equal(pulled, out) and torch.equal(again, out)
-                out = pulled
             gathered = [torch.empty_like(out) for _ in range(world)]
             dist.all_gather(gathered, out)  # test-only
             full = torch.cat(gathered, dim=2)
@@ -84,7 +76,6 @@ def _worker(rank, world, port, mode, q, k, v, scale, out_path):
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
 @pytest.mark.parametrize("mode,shape", [("bh", (2, 5, 640, 128)), ("ring", (1, 4, 1024, 128)), ("ring", (2, 2, 768, 64)),
-                                        ("pull", (1, 4, 1024, 128)), ("pull", (2, 3, 512, 64)),
                                         ("native", (1, 4, 1024, 128)), ("native", (2, 3, 768, 64)), ("native", (1, 2, 4096, 128))])
 def test_two_gpu_paths_match_oracle(tmp_path, oracle, mode, shape):
     B, H, N, D = shape
