@@ -14,8 +14,9 @@
   are in flight from the start and none waits for an earlier one; or, with `peers=`, `fa_ring_forward_pull`: no
   NCCL at all, the attention kernel's spare warps load the next shard from its owner's memory over NVLink).
   The Python-orchestrated `ring_attention` below is kept as the independent implementation it is tested against:
-  it passes shards rank -> rank+1 with NCCL send/recv.  (Round 1's copy-engine variant is gone: cudaMemcpyAsync
-  from a peer mapping runs at 25 GB/s on this platform.)
+  it passes shards rank -> rank+1 with NCCL send/recv.  (Round 1's copy-engine variant is gone: it copied from
+  mappings opened on the OWNER's device index -- what torch's tensor sharing produces -- which the driver stages at
+  25 GB/s; opened in the consumer's context the same copy runs at 725 GB/s, and kernels can load from the mapping.)
 
 Only the ring communicates; `torch.distributed` is plumbing (NCCL on GPUs, gloo in the CPU tests, which
 exercise the schedule with an injected step function).

@@ -130,8 +130,9 @@ int fa_ring_forward(const void* Q, const void* K, const void* V, void* O, int B,
  * lane, every CTA its 1 / grid slice).  One launch per step on the caller's stream and nothing else: no NCCL, no
  * second stream, no events, no SM taken from the attention kernel (NCCL's send/recv CTAs cannot share an SM with a
  * 227 KB attention CTA, and at 8 ranks its point-to-point exchange ran at ~70 GB/s per peer: 14.3 ms for config 4
- * against 7.7 ms of compute), and no rank waits for another inside the call.  The copy engines are not an
- * alternative on this platform: cudaMemcpyAsync from a peer mapping measured 25 GB/s.
+ * against 7.7 ms of compute), and no rank waits for another inside the call.  (The copy engines would also do:
+ * cudaMemcpyAsync from a mapping opened in the consumer's context measured 725 GB/s, 691 GB/s next to a running
+ * attention kernel; the fused form needs no second stream and no events.)
  * Arithmetic, visiting order and workspace layout are those of fa_ring_forward (two receive buffers are enough):
  * the two return bit-identical results.
  * The caller orders the ranks around the call: every rank's K / V must be complete before any rank starts, and
@@ -150,8 +151,8 @@ int fa_enable_peer_access(int peer_device);
  *                                        often live in one allocation);
  *   fa_ipc_close(base)                   unmaps; the owner may free the allocation afterwards.
  * The mapping must be opened in the CONSUMER's context: a mapping opened on the owner's device index (what a
- * framework's tensor sharing does) can be copied from by the driver (staged, 25 GB/s measured) but faults when a
- * kernel of another GPU loads from it.
+ * framework's tensor sharing does) can be copied from by the driver (staged: 25 GB/s measured, against 725 GB/s for
+ * a consumer-context mapping) but faults when a kernel of another GPU loads from it.
  */
 int fa_ipc_export(const void* ptr, unsigned char* handle /* [64] */, unsigned long long* offset);
 int fa_ipc_open(const unsigned char* handle /* [64] */, void** base);
