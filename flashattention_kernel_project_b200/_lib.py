@@ -30,6 +30,7 @@ SIGNATURES = {
                                      ctypes.POINTER(c_void_p), c_void_p, ctypes.c_size_t, c_void_p]),
     "gemm_fused_epilogue": (c_int, [c_void_p] * 5 + [c_int] * 3 + [c_void_p]),
     "gemm_fused_epilogue_act": (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_void_p]),
+    "gemm_fused_epilogue_f32": (c_int, [c_void_p] * 5 + [c_int] * 4 + [c_void_p]),
     "gemm_batched_strided": (c_int, [c_void_p] * 3 + [c_int] * 4 + [ctypes.c_longlong] * 6 + [c_int, c_float, c_void_p]),
     "gemm_batched": (c_int, [c_void_p] * 3 + [c_int] * 5 + [c_float, c_void_p]),
     "softmax_rows": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),

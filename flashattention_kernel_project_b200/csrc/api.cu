@@ -8,6 +8,7 @@
 // every failure is a return code.
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -24,6 +25,12 @@
 namespace {
 
 using namespace fa;
+
+#define FA_CUDA_TRY(expr)                               \
+  do {                                                  \
+    cudaError_t e__ = (expr);                           \
+    if (e__ != cudaSuccess) return static_cast<int>(e__); \
+  } while (0)
 
 constexpr int kMaxDevices = 64;
 constexpr int kMaxRingWorld = 64;
@@ -133,7 +140,7 @@ struct DeviceState {
   bool probed = false;
   bool is_sm100 = false;
   int sm_count = 0;
-  bool attr_fa64 = false, attr_fa128 = false, attr_gemm = false, attr_gemm_t = false;
+  bool attr_fa64 = false, attr_fa128 = false, attr_gemm = false, attr_gemm_t = false, attr_gemm_split = false;
   // stream-ordered pool for the attention kernel's tail workspace (allocated and freed on the caller's stream
   // around the launch, so concurrent launches on different streams and captured graphs each own theirs)
   bool pool_tried = false;
@@ -500,9 +507,9 @@ int run_gemm(const GemmCall& c, void* stream) {
   const int grid = 2 * static_cast<int>(tiles < pairs_max ? tiles : pairs_max);
   const cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (c.trans_b)
-    gemm_fused_kernel<true><<<grid, GemmCfg::kThreads, GemmCfg::kSmemBytes, s>>>(ma, mb, mr, mc, p);
+    gemm_fused_kernel<true><<<grid, GemmCfg::kThreads, GemmCfg::kSmemBytes, s>>>(ma, mb, mr, mc, ma, mb, p);
   else
-    gemm_fused_kernel<false><<<grid, GemmCfg::kThreads, GemmCfg::kSmemBytes, s>>>(ma, mb, mr, mc, p);
+    gemm_fused_kernel<false><<<grid, GemmCfg::kThreads, GemmCfg::kSmemBytes, s>>>(ma, mb, mr, mc, ma, mb, p);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   const cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? FA_OK : static_cast<int>(e);
@@ -512,6 +519,88 @@ int run_gemm(const void* A, const void* Bm, const float* bias, const float* resi
              void* stream) {
   const GemmCall c{A, Bm, bias, residual, C, 1, M, N, K, false, GEMM_ACT_RELU, 1.0f};
   return run_gemm(c, stream);
+}
+
+// fp32 operands through the tf32 tensor path, split into (hi, lo) pairs ("3xTF32"): see GemmCfgT in gemm_fused.cuh.
+// Scratch for the four split operands (2 x (M*K + N*K) floats) comes from the stream-ordered pool and is released on
+// the stream after the GEMM.
+int run_gemm_f32(const float* A, const float* Bm, const float* bias, const float* residual, float* C, int M, int N,
+                 int K, int act, void* stream) {
+  using Cfg = GemmCfgT<true>;
+  if (M <= 0 || N <= 0 || K <= 0) return FA_ERR_BAD_SHAPE;
+  if (A == nullptr || Bm == nullptr || C == nullptr) return FA_ERR_NULL_POINTER;
+  if ((N & 3) != 0 || (K & 3) != 0) return FA_ERR_MISALIGNED;  // fp32 rows must be 16-byte multiples
+  if (!aligned16(A) || !aligned16(Bm) || !aligned16(C) || !aligned16(bias) || !aligned16(residual)) return FA_ERR_MISALIGNED;
+  if (act < GEMM_ACT_IDENTITY || act > GEMM_ACT_SILU) return FA_ERR_BAD_ARGUMENT;
+  DeviceState* st = nullptr;
+  int rc = current_device_state(&st);
+  if (rc != FA_OK) return rc;
+  if (st->pool == nullptr) return FA_ERR_NO_DEVICE;
+  const cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t a_elems = static_cast<size_t>(M) * K, b_elems = static_cast<size_t>(N) * K;
+  const size_t a_bytes = (a_elems * 4 + 255) & ~static_cast<size_t>(255), b_bytes = (b_elems * 4 + 255) & ~static_cast<size_t>(255);
+  void* scratch = nullptr;
+  FA_CUDA_TRY(cudaMallocFromPoolAsync(&scratch, 2 * a_bytes + 2 * b_bytes, st->pool, s));
+  float* const a_hi = static_cast<float*>(scratch);
+  float* const a_lo = reinterpret_cast<float*>(static_cast<char*>(scratch) + a_bytes);
+  float* const b_hi = reinterpret_cast<float*>(static_cast<char*>(scratch) + 2 * a_bytes);
+  float* const b_lo = reinterpret_cast<float*>(static_cast<char*>(scratch) + 2 * a_bytes + b_bytes);
+  auto fail = [&](int code) {
+    cudaFreeAsync(scratch, s);
+    return code;
+  };
+  {
+    const size_t n4 = a_elems / 4;
+    const unsigned blocks = static_cast<unsigned>(std::min<size_t>((n4 + 255) / 256, static_cast<size_t>(st->sm_count) * 16));
+    gemm_split_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<const float4*>(A), reinterpret_cast<float4*>(a_hi),
+                                             reinterpret_cast<float4*>(a_lo), n4);
+    const dim3 tgrid((N + 31) / 32, (K + 31) / 32);
+    gemm_split_transpose_kernel<<<tgrid, dim3(32, 8), 0, s>>>(Bm, b_hi, b_lo, K, N);
+    g_launches.fetch_add(2, std::memory_order_relaxed);
+  }
+  CUtensorMap ma, mb, ma2, mb2, mr, mc;
+  const uint64_t da[3] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M), 1};
+  const uint64_t db[3] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N), 1};
+  const uint32_t box[3] = {32, 128, 1};  // 32 fp32 = one 128-byte swizzle row
+  if ((rc = make_map(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a_hi, 3, da, box)) != FA_OK) return fail(rc);
+  if ((rc = make_map(&ma2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a_lo, 3, da, box)) != FA_OK) return fail(rc);
+  if ((rc = make_map(&mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, b_hi, 3, db, box)) != FA_OK) return fail(rc);
+  if ((rc = make_map(&mb2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, b_lo, 3, db, box)) != FA_OK) return fail(rc);
+  const uint64_t dc[3] = {static_cast<uint64_t>(N), static_cast<uint64_t>(M), 1};
+  const uint32_t bc[3] = {Cfg::kEpiCols, Cfg::kBM, 1};
+  if ((rc = make_map(&mc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, C, 3, dc, bc)) != FA_OK) return fail(rc);
+  if (residual != nullptr) {
+    if ((rc = make_map(&mr, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, residual, 3, dc, bc)) != FA_OK) return fail(rc);
+  } else {
+    mr = mc;
+  }
+  {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if ((rc = ensure_smem_attr(&st->attr_gemm_split, gemm_fused_kernel<true, true>, Cfg::kSmemBytes)) != FA_OK)
+      return fail(rc);
+  }
+  GemmParams p;
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.batch = 1;
+  p.m_blocks = (M + 255) / 256;
+  p.n_blocks = (N + Cfg::kBN - 1) / Cfg::kBN;
+  p.alpha = 1.0f;
+  p.act = act;
+  p.bias = bias;
+  p.residual = residual;
+  p.C = C;
+  p.dbg = debug_channel();
+  const long long tiles = static_cast<long long>(p.m_blocks) * p.n_blocks;
+  const long long pairs_max = st->sm_count / 2;
+  const int grid = 2 * static_cast<int>(tiles < pairs_max ? tiles : pairs_max);
+  gemm_fused_kernel<true, true><<<grid, Cfg::kThreads, Cfg::kSmemBytes, s>>>(ma, mb, mr, mc, ma2, mb2, p);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  const cudaError_t ef = cudaFreeAsync(scratch, s);
+  if (e == cudaSuccess) e = ef;
+  return e == cudaSuccess ? FA_OK : static_cast<int>(e);
 }
 
 // ---- softmax ------------------------------------------------------------------------------
@@ -568,11 +657,6 @@ int scratch_get(DeviceState* st, int slot, size_t bytes, void** out) {
   return FA_OK;
 }
 
-#define FA_CUDA_TRY(expr)                               \
-  do {                                                  \
-    cudaError_t e__ = (expr);                           \
-    if (e__ != cudaSuccess) return static_cast<int>(e__); \
-  } while (0)
 
 // Inside the chunk loops of the *_host entry points: a failing call must not leave earlier chunks' copies running
 // against the caller's buffers (and the scratch, which the next call reuses) -- drain the pipeline, then return.
@@ -617,9 +701,10 @@ int host_chunk_limit() {
   }();
   return limit;
 }
-// Chunks of >= 8 MB of traffic each, at most host_chunk_limit() and at most one per unit.
+// Chunks of >= 32 MB of traffic each (8 MB per copy with four tensors: below that the per-copy cost shows, most of
+// all when 8 ranks share one host), at most host_chunk_limit() and at most one per unit.
 int host_chunks(size_t total_bytes, long long units) {
-  long long n = static_cast<long long>(total_bytes >> 23);
+  long long n = static_cast<long long>(total_bytes >> 25);
   if (n > host_chunk_limit()) n = host_chunk_limit();
   if (n > units) n = units;
   return n < 1 ? 1 : static_cast<int>(n);
@@ -993,6 +1078,11 @@ int gemm_fused_epilogue_act(const void* A, const void* Bm, const float* bias, co
                             int N, int K, int act, void* stream) {
   const GemmCall c{A, Bm, bias, residual, C, 1, M, N, K, false, act, 1.0f};
   return run_gemm(c, stream);
+}
+
+int gemm_fused_epilogue_f32(const float* A, const float* Bm, const float* bias, const float* residual, float* C, int M,
+                            int N, int K, int act, void* stream) {
+  return run_gemm_f32(A, Bm, bias, residual, C, M, N, K, act, stream);
 }
 
 int gemm_batched_strided(const void* A, const void* Bm, float* C, int batch, int M, int N, int K, long long lda,

@@ -48,18 +48,28 @@ enum GemmAct : int { GEMM_ACT_IDENTITY = 0, GEMM_ACT_RELU = 1, GEMM_ACT_GELU = 2
 __device__ __forceinline__ float gemm_act_gelu(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float gemm_act_silu(float x) { return x / (1.f + expf(-x)); }
 
-struct GemmCfg {
+// kSplit = false: fp16 operands, one tcgen05.mma pass per k-block (the tensor-core GEMM of the reference).
+// kSplit = true : fp32 operands as tf32 (hi, lo) PAIRS -- "3xTF32": A*B ~ A_lo*B_hi + A_hi*B_lo + A_hi*B_hi recovers
+//                 fp32-level products from the tf32 tensor path (the reference's fp32 sibling gemm_tiled_fused_kernel,
+//                 GEMM/gemm_fused_epilogue/gemm_fused_epilogue.cu:44-111, is a scalar-FMA kernel).  Four operand tiles
+//                 per stage (A_hi, A_lo, B_hi, B_lo), three MMA passes, both operands K-major (B arrives transposed).
+template <bool kSplit>
+struct GemmCfgT {
   static constexpr int kBM = 128;   // rows per CTA (256 per pair)
-  static constexpr int kBN = 256, kBK = 64;
-  static constexpr int kStages = 5;
-  static constexpr int kABytes = kBM * kBK * 2;            // 16 KB: one 128B-swizzled box
-  static constexpr int kBBoxBytes = 64 * 128;              // 64 k-rows x 128 B (64 n columns)
-  static constexpr int kBBytes = (kBN / 2 / 64) * kBBoxBytes;  // this CTA's half of B: 16 KB
-  static constexpr int kStageBytes = kABytes + kBBytes;    // 32 KB per CTA
+  static constexpr int kBN = 256;
+  static constexpr int kElemBytes = kSplit ? 4 : 2;
+  static constexpr int kBK = 128 / kElemBytes;             // one 128-byte swizzle row of K per k-block: 64 fp16 / 32 fp32
+  static constexpr int kKPerMma = 32 / kElemBytes;         // 16 (f16) / 8 (tf32)
+  static constexpr int kStages = kSplit ? 3 : 5;
+  static constexpr int kABytes = kBM * 128;                // 16 KB: one 128B-swizzled box
+  static constexpr int kBBoxBytes = 64 * 128;              // fp16 [K,N] form: 64 k-rows x 128 B (64 n columns)
+  static constexpr int kBBytes = (kBN / 2) * 128;          // this CTA's half of B: 16 KB
+  static constexpr int kOperandSets = kSplit ? 2 : 1;      // (hi, lo)
+  static constexpr int kStageBytes = kOperandSets * (kABytes + kBBytes);  // 32 KB / 64 KB per CTA
   // epilogue ring: kEpiBufs buffers of 128 rows x 32 fp32 columns (one 128B-swizzled TMA box each).  A buffer
   // receives a residual block by TMA, is updated in place with the accumulator, and leaves by TMA store.
   static constexpr int kEpiCols = 32;
-  static constexpr int kEpiBufs = 4;
+  static constexpr int kEpiBufs = kSplit ? 2 : 4;
   static constexpr int kEpiBufBytes = kBM * kEpiCols * 4;  // 16 KB
   static constexpr int kChunksPerTile = kBN / kEpiCols;    // 8
   static constexpr int kOffBar = kStages * kStageBytes;
@@ -71,6 +81,7 @@ struct GemmCfg {
   static constexpr int kGroupN = 8;  // rasterisation: bands of 8 n-blocks, m fastest inside a band
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
 };
+using GemmCfg = GemmCfgT<false>;
 
 enum : uint32_t { SITE_G_EMPTY = 0x21, SITE_G_FULL, SITE_G_TEMPTY, SITE_G_TFULL, SITE_G_RFULL };
 
@@ -102,6 +113,19 @@ __device__ __forceinline__ void umma_ss_2sm(uint32_t tmem_d, uint64_t desc_a, ui
       "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+__device__ __forceinline__ void umma_ss_2sm_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// kind::tf32 instruction descriptor: as umma_idesc_f16 with A / B format 2 (TF32); both operands K-major
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(uint32_t M, uint32_t N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 // arrive (once all prior tcgen05 ops of this thread completed) on the barrier at this offset in BOTH CTAs
 __device__ __forceinline__ void umma_commit_2sm_mc(uint64_t* bar) {
@@ -140,12 +164,15 @@ __device__ __forceinline__ void gemm_tile_coords(int tile, const GemmParams& p, 
 
 // kTransB = false: B is [K,N] row-major (an MN-major operand, two 64-column boxes per CTA and k-block);
 // kTransB = true:  B is [N,K] row-major, C = A * B^T (a K-major operand like A, one 128-row box).
-template <bool kTransB>
+// kSplit (see GemmCfgT): mapA / mapB are the tf32 HI parts, mapA2 / mapB2 the LO parts (fp32 [M,K] and [N,K]).
+template <bool kTransB, bool kSplit = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
 gemm_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                   const __grid_constant__ CUtensorMap mapR, const __grid_constant__ CUtensorMap mapC,
+                  const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB2,
                   const GemmParams p) {
-  using Cfg = GemmCfg;
+  static_assert(!kSplit || kTransB, "the split-fp32 path takes B transposed (K-major)");
+  using Cfg = GemmCfgT<kSplit>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBar);
   uint64_t* const full = bars;                        // [kStages] TMA (both CTAs) -> MMA; used in the leader only
@@ -182,6 +209,10 @@ gemm_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     prefetch_tensormap(&mapB);
     prefetch_tensormap(&mapR);
     prefetch_tensormap(&mapC);
+    if constexpr (kSplit) {
+      prefetch_tensormap(&mapA2);
+      prefetch_tensormap(&mapB2);
+    }
   }
   if (warp == 2) {
     tmem_alloc_2sm(tmem_slot, 512);
@@ -210,7 +241,12 @@ gemm_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           tma_load_3d_2sm(a_dst, &mapA, &full[s], kb * Cfg::kBK, mb * 256 + static_cast<int>(rank) * Cfg::kBM, bz,
                           kEvictNormal);
           const int n0 = nb * Cfg::kBN + static_cast<int>(rank) * (Cfg::kBN / 2);  // this CTA's half of the B block
-          if constexpr (kTransB) {
+          if constexpr (kSplit) {  // stage = A_hi | B_hi | A_lo | B_lo
+            tma_load_3d_2sm(b_dst, &mapB, &full[s], kb * Cfg::kBK, n0, bz, kEvictNormal);
+            tma_load_3d_2sm(b_dst + Cfg::kBBytes, &mapA2, &full[s], kb * Cfg::kBK,
+                            mb * 256 + static_cast<int>(rank) * Cfg::kBM, bz, kEvictNormal);
+            tma_load_3d_2sm(b_dst + Cfg::kBBytes + Cfg::kABytes, &mapB2, &full[s], kb * Cfg::kBK, n0, bz, kEvictNormal);
+          } else if constexpr (kTransB) {
             tma_load_3d_2sm(b_dst, &mapB, &full[s], kb * Cfg::kBK, n0, bz, kEvictNormal);
           } else {
 #pragma unroll
@@ -224,7 +260,7 @@ gemm_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   } else if (warp == 1) {
     // -------------------------------- MMA issuer (leader CTA) -------------------------
     if (rank == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(256, Cfg::kBN, 0, kTransB ? 0 : 1);
+      constexpr uint32_t idesc = kSplit ? umma_idesc_tf32(256, Cfg::kBN) : umma_idesc_f16(256, Cfg::kBN, 0, kTransB ? 0 : 1);
       int it = 0, local = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs, ++local) {
         const int acc = local & 1;
@@ -240,11 +276,23 @@ gemm_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           const uint32_t a0 = smem_u32(smem + s * Cfg::kStageBytes);
           const uint32_t b0 = a0 + Cfg::kABytes;
           if (elect_one()) {
+            if constexpr (kSplit) {
+              // small terms first: A_lo*B_hi, A_hi*B_lo, then A_hi*B_hi -- all into the same fp32 accumulator
+              const uint32_t a_lo = b0 + Cfg::kBBytes, b_lo = a_lo + Cfg::kABytes;
+              const uint32_t pa[3] = {a_lo, a0, a0}, pb[3] = {b0, b_lo, b0};
 #pragma unroll
-            for (int ks = 0; ks < Cfg::kBK / 16; ++ks) {
-              const uint64_t db = kTransB ? umma_desc_sw128(b0 + ks * 32, 16, 1024)
-                                          : umma_desc_sw128(b0 + ks * 2048, Cfg::kBBoxBytes, 1024);
-              umma_ss_2sm(d, umma_desc_sw128(a0 + ks * 32, 16, 1024), db, idesc, (kb | ks) ? 1u : 0u);
+              for (int pass = 0; pass < 3; ++pass)
+#pragma unroll
+                for (int ks = 0; ks < Cfg::kBK / Cfg::kKPerMma; ++ks)
+                  umma_ss_2sm_tf32(d, umma_desc_sw128(pa[pass] + ks * 32, 16, 1024),
+                                   umma_desc_sw128(pb[pass] + ks * 32, 16, 1024), idesc, (kb | ks | pass) ? 1u : 0u);
+            } else {
+#pragma unroll
+              for (int ks = 0; ks < Cfg::kBK / Cfg::kKPerMma; ++ks) {
+                const uint64_t db = kTransB ? umma_desc_sw128(b0 + ks * 32, 16, 1024)
+                                            : umma_desc_sw128(b0 + ks * 2048, Cfg::kBBoxBytes, 1024);
+                umma_ss_2sm(d, umma_desc_sw128(a0 + ks * 32, 16, 1024), db, idesc, (kb | ks) ? 1u : 0u);
+              }
             }
             umma_commit_2sm_mc(&empty[s]);
             if (kb == num_kb - 1) umma_commit_2sm_mc(&tfull[acc]);
@@ -341,6 +389,50 @@ gemm_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   cluster_sync_all();  // no CTA of the pair may exit (or free TMEM) while the other still signals it
   tc_fence_after();
   if (warp == 2) tmem_dealloc_2sm(tmem_base, 512);
+}
+
+// ---- pre-pass of the split-fp32 path: x = hi + lo with hi = RN_tf32(x) (low 13 mantissa bits zero, so whatever
+// rounding the tensor core applies to its 32-bit inputs leaves hi untouched) and lo = x - hi (exact in fp32).
+__device__ __forceinline__ void tf32_split(float x, float& hi, float& lo) {
+  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+  lo = x - hi;
+}
+// A [rows, cols] -> hi, lo of the same shape; cols % 4 == 0, 16-byte aligned
+__global__ void __launch_bounds__(256) gemm_split_kernel(const float4* __restrict__ x, float4* __restrict__ hi,
+                                                         float4* __restrict__ lo, size_t n4) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float4 v = __ldcs(x + i);
+    float4 h, l;
+    tf32_split(v.x, h.x, l.x);
+    tf32_split(v.y, h.y, l.y);
+    tf32_split(v.z, h.z, l.z);
+    tf32_split(v.w, h.w, l.w);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+// B [K, N] row-major -> hi, lo TRANSPOSED to [N, K] (the K-major operand the tensor core reads like A);
+// 32 x 32 tiles through shared memory, block (32, 8)
+__global__ void __launch_bounds__(256) gemm_split_transpose_kernel(const float* __restrict__ b, float* __restrict__ hi,
+                                                                   float* __restrict__ lo, int K, int N) {
+  __shared__ float th[32][33], tl[32][33];
+  const int n0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int k = k0 + r, n = n0 + threadIdx.x;
+    float h = 0.f, l = 0.f;
+    if (k < K && n < N) tf32_split(__ldcs(b + static_cast<size_t>(k) * N + n), h, l);
+    th[r][threadIdx.x] = h;
+    tl[r][threadIdx.x] = l;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int n = n0 + r, k = k0 + threadIdx.x;
+    if (n < N && k < K) {
+      hi[static_cast<size_t>(n) * K + k] = th[threadIdx.x][r];
+      lo[static_cast<size_t>(n) * K + k] = tl[threadIdx.x][r];
+    }
+  }
 }
 
 }  // namespace fa

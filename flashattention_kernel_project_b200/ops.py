@@ -166,6 +166,30 @@ def gemm_fused_epilogue(a, b, bias=None, residual=None, out=None, stream=None, a
     return out
 
 
+def gemm_fused_epilogue_f32(a, b, bias=None, residual=None, out=None, stream=None, act="relu"):
+    """C = act(A @ B + bias) + residual with fp32 operands: A [M,K], B [K,N] (gemm_tiled_fused_kernel,
+    GEMM/gemm_fused_epilogue/gemm_fused_epilogue.cu:44-111), on the tensor cores as split tf32 pairs (3xTF32)."""
+    _require_cuda(a, "A")
+    _require_cuda(b, "B")
+    if act not in ACTIVATIONS:
+        raise ValueError(f"act must be one of {sorted(ACTIVATIONS)}")
+    if a.dim() != 2 or b.dim() != 2 or a.shape[1] != b.shape[0]:
+        raise ValueError("A must be [M, K] and B [K, N]")
+    M, K = int(a.shape[0]), int(a.shape[1])
+    N = int(b.shape[1])
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    lib = load_library()
+    with torch.cuda.device(a.device):
+        dev = a.device
+        check(lib.gemm_fused_epilogue_f32(_dev_ptr(a, torch.float32, "A"), _dev_ptr(b, torch.float32, "B", (K, N), dev),
+                                          _dev_ptr(bias, torch.float32, "bias", (N,), dev),
+                                          _dev_ptr(residual, torch.float32, "residual", (M, N), dev),
+                                          _dev_ptr(out, torch.float32, "C", (M, N), dev), M, N, K, ACTIVATIONS[act],
+                                          _stream_ptr(stream)), "gemm_fused_epilogue_f32")
+    return out
+
+
 def _strided3(t, dtype, name, device=None):
     """(pointer, row pitch, batch stride) of a [batch, rows, cols] tensor whose last dimension is contiguous: a dense
     tensor or a view of one (a head of a [B,N,H,D] tensor, a sub-matrix, a padded leading dimension)."""

@@ -184,6 +184,23 @@ int gemm_fused_epilogue_act(const void* A, const void* Bm, const float* bias, co
                             int M, int N, int K, int act, void* stream);
 
 /*
+ * The fp32-operand sibling: C = act(A*B + bias[col]) + residual with A fp32 [M,K], Bm fp32 [K,N] (row-major, not
+ * transposed), fp32 bias / residual / C; K % 4 == 0 and N % 4 == 0.
+ * Replaces: gemm_tiled_fused_kernel(A, B, bias, residual, C, M, N, K)
+ *   (GEMM/gemm_fused_epilogue/gemm_fused_epilogue.cu:44-111: 32 x 32 shared-memory tiles, scalar fp32 FMA, the same
+ *    bias -> ReLU -> residual epilogue, :88-110), act = FA_ACT_RELU.
+ * Runs on the tensor cores at fp32-level accuracy: every operand is split into two tf32 numbers, x = hi + lo with
+ * hi = x rounded to tf32 and lo = x - hi (exact), and the product is accumulated as A_lo*B_hi + A_hi*B_lo + A_hi*B_hi
+ * ("3xTF32"; the dropped lo*lo term is below 2^-21 relative) by the same persistent CTA-pair kernel as
+ * gemm_fused_epilogue (tcgen05.mma kind::tf32, cta_group::2, fp32 accumulators in TMEM, TMA epilogue).  A plain tf32
+ * GEMM would miss the tolerance (2^-11 per operand: ~4e-3 absolute at K = 1024 with the reference's uniform(-1,1)
+ * fixture).  A short pre-pass writes the four split operands (B transposed to [N,K] on the way) into scratch taken
+ * from the library's stream-ordered pool for the duration of the call: 2 x (M*K + N*K) floats.
+ */
+int gemm_fused_epilogue_f32(const float* A, const float* Bm, const float* bias, const float* residual, float* C,
+                            int M, int N, int K, int act, void* stream);
+
+/*
  * Batched plain GEMM with a scale: C[z] = alpha * A[z] * op(B[z]) for z in [0, batch), no bias / activation.
  *   A fp16 [batch,M,K]; Bm fp16 [batch,K,N] if trans_b == 0, fp16 [batch,N,K] if trans_b != 0 (C = alpha*A*B^T);
  *   C fp32 [batch,M,N]; all row-major and densely packed; K % 8 == 0 and N % 8 == 0.

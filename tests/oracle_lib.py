@@ -100,7 +100,8 @@ class Oracle:
         return out
 
     def gemm_fused(self, a, b, bias, residual, row_begin=0, row_end=None, nthreads=0):
-        """fp32 operands, full [M, N] result buffer; only rows [row_begin, row_end) are computed."""
+        """fp32 operands, full [M, N] result buffer; only rows [row_begin, row_end) are computed.  Restates both
+        cpu_gemm_fused_ref functions of the reference (tensor-core file :136-155, fp32 file :116-136: same code)."""
         a = np.ascontiguousarray(a, dtype=np.float32)
         b = np.ascontiguousarray(b, dtype=np.float32)
         M, K = a.shape
@@ -218,6 +219,9 @@ class RefCpu:
         self.gemm = RefLib("gemm_fused").L
         self.gemm.ref_gemm_fused_cpu.argtypes = [_f32p] * 5 + [c_int] * 3
         self.gemm.ref_gemm_fused_fill.argtypes = [ctypes.c_uint] + [_f32p, c_size_t] * 4
+        self.gemm32 = RefLib("gemm_fp32_fused").L if ref_available("gemm_fp32_fused") else None
+        if self.gemm32 is not None:
+            self.gemm32.ref_gemm_fp32_fused_cpu.argtypes = [_f32p] * 5 + [c_int] * 3
         # added after the first fixtures were cut: absent in an older prebuilt oracle/_ref
         self.bgemm = RefLib("gemm_batched").L if ref_available("gemm_batched") else None
         if self.bgemm is not None:
@@ -270,6 +274,15 @@ class RefCpu:
         out = np.empty((BH, N, D), dtype=np.float32)
         self.sb.ref_softmax_block_flashattn_ref(*(np.ascontiguousarray(x, dtype=np.float32) for x in (q, k, v)), out,
                                                 N, D, BH, float(scale))
+        return out
+
+    def gemm_fp32_fused_cpu(self, a, b, bias, residual):
+        """cpu_gemm_fused_ref of the fp32 sibling (GEMM/gemm_fused_epilogue/gemm_fused_epilogue.cu:116-136)."""
+        M, K = a.shape
+        N = b.shape[1]
+        out = np.empty((M, N), dtype=np.float32)
+        self.gemm32.ref_gemm_fp32_fused_cpu(*(np.ascontiguousarray(x, dtype=np.float32) for x in (a, b, bias, residual)),
+                                            out, M, N, K)
         return out
 
     def gemm_fused_cpu(self, a, b, bias, residual):
@@ -329,6 +342,9 @@ class RefGpu:
         self.v75.ref_v7_5_launch.argtypes = [vp, vp, vp, vp, c_int, c_int, c_float, vp]
         self.gemm = RefLib("gemm_fused").L
         self.gemm.ref_gemm_fused_launch.argtypes = [vp, vp, vp, vp, vp, c_int, c_int, c_int, vp]
+        self.gemm32 = RefLib("gemm_fp32_fused").L if ref_available("gemm_fp32_fused") else None
+        if self.gemm32 is not None:
+            self.gemm32.ref_gemm_fp32_fused_launch.argtypes = [vp, vp, vp, vp, vp, c_int, c_int, c_int, vp]
         self.softmax = RefLib("softmax_naive").L
         self.softmax.ref_softmax_naive_launch.argtypes = [vp, vp, c_int, c_int, vp]
         self.bgemm = RefLib("gemm_batched").L
@@ -378,6 +394,14 @@ class RefGpu:
         self._chk(self.gemm.ref_gemm_fused_launch(a.data_ptr(), b.data_ptr(), bias.data_ptr() if bias is not None else None,
                                                   residual.data_ptr() if residual is not None else None, out.data_ptr(),
                                                   M, N, K, stream), "gemm_fused")
+
+    def gemm_fp32_fused(self, a, b, bias, residual, out, stream=0):
+        """gemm_tiled_fused_kernel (fp32 operands) on device tensors."""
+        M, K = a.shape
+        N = b.shape[1]
+        self._chk(self.gemm32.ref_gemm_fp32_fused_launch(a.data_ptr(), b.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                                         residual.data_ptr() if residual is not None else None,
+                                                         out.data_ptr(), M, N, K, stream), "gemm_tiled_fused_kernel")
 
     def softmax_naive(self, x, out, stream=0):
         self._chk(self.softmax.ref_softmax_naive_launch(x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], stream),

@@ -185,3 +185,16 @@ def test_oracle_bit_exact_against_compiled_reference(oracle):
         assert np.array_equal(r.gemm_batched_cpu(ab, bb), oracle.gemm_batched(ab, bb))
         qq, kk = rng.standard_normal((3, 20, 24)).astype(np.float32), rng.standard_normal((3, 20, 24)).astype(np.float32)
         assert np.array_equal(r.qk_cpu(qq, kk, 0.2041), oracle.qk_scores(qq, kk, 0.2041))
+
+
+def test_fp32_fused_gemm_oracle_matches_the_reference_fp32_file(oracle):
+    """fa_oracle_gemm_fused also restates cpu_gemm_fused_ref of the fp32 sibling program
+    (GEMM/gemm_fused_epilogue/gemm_fused_epilogue.cu:116-136): bit-exact against that function compiled unmodified."""
+    if not ref_available("gemm_fp32_fused"):
+        pytest.skip("oracle/_ref/libref_gemm_fp32_fused.so not built")
+    ref = RefCpu()
+    rng = np.random.default_rng(42)
+    M, N, K = 70, 96, 132
+    a, b = rng.uniform(-1, 1, (M, K)).astype(np.float32), rng.uniform(-1, 1, (K, N)).astype(np.float32)
+    bias, res = rng.uniform(-1, 1, N).astype(np.float32), rng.uniform(-1, 1, (M, N)).astype(np.float32)
+    assert np.array_equal(oracle.gemm_fused(a, b, bias, res), ref.gemm_fp32_fused_cpu(a, b, bias, res))
