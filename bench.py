@@ -527,10 +527,15 @@ def reference_gpu_kernels(torch, dev):
                 torch, lambda: ref.streaming_mw(ver, q16, k16, v16, o16, 0.25, stream=s_cur()))
         out["d16_native_B1024_M16_L128_gpu_time"] = entry
     q1, o1 = q16[:, 0].contiguous(), torch.zeros((1024, 16), device=dev)
+    s_cur = lambda: torch.cuda.current_stream().cuda_stream
+    f_ours = lambda: fa.fa_forward_cross(q1.view(1, 1024, 1, 16), k16[None], v16[None], 0.25, out=o1.view(1, 1024, 1, 16))
     out["v7_5_native_B1024_S128_D16_single_query"] = {
         "reference_us": timeit(lambda: ref.v7_5_kernel(q1, k16, v16, o1), 200) * 1e3,
-        "ours_us": timeit(lambda: fa.fa_forward_cross(q1.view(1, 1024, 1, 16), k16[None], v16[None], 0.25,
-                                                      out=o1.view(1, 1024, 1, 16)), 200) * 1e3}
+        "ours_us": timeit(f_ours, 200) * 1e3,
+        # GPU time per launch with 20 launches in one CUDA graph: the host cost of a call (Python, ctypes, launch) is
+        # longer than either kernel, so only this figure compares the kernels
+        "reference_cuda_graph_us": graph_time_us(torch, lambda: ref.v7_5_kernel(q1, k16, v16, o1, stream=s_cur())),
+        "ours_cuda_graph_us": graph_time_us(torch, f_ours)}
     B, H, N, D = 4, 16, 1024, 64
     q, k, v = ((torch.rand((B, H, N, D), device=dev) * 2 - 1).half() for _ in range(3))
     o = torch.zeros((B, H, N, D), device=dev)
@@ -549,6 +554,15 @@ def reference_gpu_kernels(torch, dev):
     ms = timeit(lambda: ref.gemm_fused(a, b, bias, res, c), 2)
     out["wmma_gemm_fused_8192"] = {"ms": ms, "tflops": 2.0 * M ** 3 / ms / 1e9}
     del a, b, res, c
+    if ref_available("gemm_fp32_fused"):  # the fp32 sibling at its harness shape (1024^3) and at 4096^3
+        for Mf in (1024, 4096):
+            af, bf = (torch.rand((Mf, Mf), device=dev) * 2 - 1 for _ in range(2))
+            biasf, resf, cf = torch.rand((Mf,), device=dev), torch.rand((Mf, Mf), device=dev), torch.empty((Mf, Mf), device=dev)
+            ms_r = timeit(lambda: ref.gemm_fp32_fused(af, bf, biasf, resf, cf), 3)
+            ms_o = timeit(lambda: fa.gemm_fused_epilogue_f32(af, bf, biasf, resf, out=cf), 20)
+            out[f"gemm_fp32_fused_{Mf}"] = {"reference_tiled_fp32_tflops": 2.0 * Mf ** 3 / ms_r / 1e9,
+                                            "ours_split_tf32_tflops": 2.0 * Mf ** 3 / ms_o / 1e9, "ours_ms": ms_o}
+            del af, bf, resf, cf
     x = torch.randn((16384, 4096), device=dev)
     p = torch.empty_like(x)
     ms = timeit(lambda: ref.softmax_naive(x, p), 10)
@@ -604,7 +618,35 @@ def extras(torch, fa, dev, peaks):
     f = lambda: fa.fa_forward(q1, k1, v1, 0.125, out=o1)
     for _ in range(5):
         f()
-    out["attn_cfg1_B1_H1_N128_D64"] = {"us": time_loop(torch, f, 200) / 200 * 1e3, "cuda_graph_us": graph_time_us(torch, f)}
+    import ctypes
+    lib = fa.load_library()
+    hits0, miss0 = ctypes.c_ulonglong(0), ctypes.c_ulonglong(0)
+    lib.fa_map_cache_stats(ctypes.byref(hits0), ctypes.byref(miss0))
+    us = time_loop(torch, f, 200) / 200 * 1e3
+    hits1, miss1 = ctypes.c_ulonglong(0), ctypes.c_ulonglong(0)
+    lib.fa_map_cache_stats(ctypes.byref(hits1), ctypes.byref(miss1))
+    # the same call straight through ctypes (no Python wrapper): what a C caller of the ABI pays per call
+    args = [ctypes.c_void_p(t.data_ptr()) for t in (q1, k1, v1, o1)] + [1, 1, 128, 64, ctypes.c_float(0.125),
+                                                                       ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)]
+    raw = lambda: lib.fa_forward(*args)
+    raw()
+    out["attn_cfg1_B1_H1_N128_D64"] = {"us": us, "abi_only_us": time_loop(torch, raw, 500) / 500 * 1e3,
+                                       "cuda_graph_us": graph_time_us(torch, f),
+                                       "tensor_map_cache": {"hits": hits1.value - hits0.value, "misses": miss1.value - miss0.value,
+                                                            "calls": 200}}
+    # a grid that fills less than half the SMs (one (b,h) of N = 4096: 16 items) is cut along K/V (stream-K)
+    qs, ks, vs = ((torch.rand((1, 1, 4096, 128), device=dev) * 2 - 1).half() for _ in range(3))
+    os_ = torch.empty_like(qs)
+    fs = lambda: fa.fa_forward(qs, ks, vs, 128 ** -0.5, out=os_)
+    fs()
+    cut_us = graph_time_us(torch, fs)
+    before = lib.fa_set_tail_split(0)
+    fs()
+    whole_us = graph_time_us(torch, fs)
+    lib.fa_set_tail_split(before)
+    out["attn_B1_H1_N4096_D128_sub_wave"] = {"cuda_graph_us": cut_us, "uncut_cuda_graph_us": whole_us,
+                                              "segments": int(lib.fa_plan_segments(1, 1, 4096, 4096, 148, None, 0))}
+    del qs, ks, vs, os_
     del q, k, v, o
     # the reference's batched-GEMM shape: 8 x 512^3 (gemm_4_9_tensorcore_batched.cu:30-33)
     ab = (torch.rand((8, 512, 512), device=dev) * 2 - 1).half()

@@ -48,6 +48,20 @@ enum GemmAct : int { GEMM_ACT_IDENTITY = 0, GEMM_ACT_RELU = 1, GEMM_ACT_GELU = 2
 __device__ __forceinline__ float gemm_act_gelu(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float gemm_act_silu(float x) { return x / (1.f + expf(-x)); }
 
+// Build knobs of the tile walk and the L2 policy of the operand loads (scripts/sustained_ab_gemm.py ranks them).
+// A wave of 74 CTA pairs covers ~9 m-blocks x kGroupN n-blocks; the next wave moves down the SAME n-band, so the B
+// panels of a band are re-read wave after wave while every A panel is used by one wave per band: B is worth keeping in
+// L2 (evict-last), A is a stream (evict-first).
+#ifndef FA_GEMM_GROUP_N
+#define FA_GEMM_GROUP_N 8
+#endif
+#ifndef FA_GEMM_HINT_A
+#define FA_GEMM_HINT_A kEvictNormal
+#endif
+#ifndef FA_GEMM_HINT_B
+#define FA_GEMM_HINT_B kEvictNormal
+#endif
+
 // kSplit = false: fp16 operands, one tcgen05.mma pass per k-block (the tensor-core GEMM of the reference).
 // kSplit = true : fp32 operands as tf32 (hi, lo) PAIRS -- "3xTF32": A*B ~ A_lo*B_hi + A_hi*B_lo + A_hi*B_hi recovers
 //                 fp32-level products from the tf32 tensor path (the reference's fp32 sibling gemm_tiled_fused_kernel,
@@ -78,7 +92,7 @@ struct GemmCfgT {
   static constexpr int kOffEpi = (kOffTmem + 16 + 1023) / 1024 * 1024;
   static constexpr int kSmemBytes = kOffEpi + kEpiBufs * kEpiBufBytes;
   static constexpr int kThreads = 256;
-  static constexpr int kGroupN = 8;  // rasterisation: bands of 8 n-blocks, m fastest inside a band
+  static constexpr int kGroupN = FA_GEMM_GROUP_N;  // rasterisation: bands of n-blocks, n fastest inside a band
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
 };
 using GemmCfg = GemmCfgT<false>;
@@ -239,19 +253,19 @@ gemm_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         if (elect_one()) {
           if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * Cfg::kStageBytes);
           tma_load_3d_2sm(a_dst, &mapA, &full[s], kb * Cfg::kBK, mb * 256 + static_cast<int>(rank) * Cfg::kBM, bz,
-                          kEvictNormal);
+                          FA_GEMM_HINT_A);
           const int n0 = nb * Cfg::kBN + static_cast<int>(rank) * (Cfg::kBN / 2);  // this CTA's half of the B block
           if constexpr (kSplit) {  // stage = A_hi | B_hi | A_lo | B_lo
-            tma_load_3d_2sm(b_dst, &mapB, &full[s], kb * Cfg::kBK, n0, bz, kEvictNormal);
+            tma_load_3d_2sm(b_dst, &mapB, &full[s], kb * Cfg::kBK, n0, bz, FA_GEMM_HINT_B);
             tma_load_3d_2sm(b_dst + Cfg::kBBytes, &mapA2, &full[s], kb * Cfg::kBK,
-                            mb * 256 + static_cast<int>(rank) * Cfg::kBM, bz, kEvictNormal);
-            tma_load_3d_2sm(b_dst + Cfg::kBBytes + Cfg::kABytes, &mapB2, &full[s], kb * Cfg::kBK, n0, bz, kEvictNormal);
+                            mb * 256 + static_cast<int>(rank) * Cfg::kBM, bz, FA_GEMM_HINT_A);
+            tma_load_3d_2sm(b_dst + Cfg::kBBytes + Cfg::kABytes, &mapB2, &full[s], kb * Cfg::kBK, n0, bz, FA_GEMM_HINT_B);
           } else if constexpr (kTransB) {
-            tma_load_3d_2sm(b_dst, &mapB, &full[s], kb * Cfg::kBK, n0, bz, kEvictNormal);
+            tma_load_3d_2sm(b_dst, &mapB, &full[s], kb * Cfg::kBK, n0, bz, FA_GEMM_HINT_B);
           } else {
 #pragma unroll
             for (int b = 0; b < Cfg::kBN / 2 / 64; ++b)
-              tma_load_3d_2sm(b_dst + b * Cfg::kBBoxBytes, &mapB, &full[s], n0 + b * 64, kb * Cfg::kBK, bz, kEvictNormal);
+              tma_load_3d_2sm(b_dst + b * Cfg::kBBoxBytes, &mapB, &full[s], n0 + b * 64, kb * Cfg::kBK, bz, FA_GEMM_HINT_B);
           }
         }
         __syncwarp();

@@ -15,6 +15,23 @@ import torch
 from ._lib import check, load_library
 
 
+class _on(object):
+    """`with _on(device):` -- make `device` current for the call, at no cost when it already is (torch.cuda.device
+    is a ~5 us context manager; BASELINE config 1 is 4 us of GPU time)."""
+    __slots__ = ("ctx",)
+
+    def __init__(self, device):
+        self.ctx = None if device.index is None or device.index == torch.cuda.current_device() else torch.cuda.device(device)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *a):
+        if self.ctx is not None:
+            self.ctx.__exit__(*a)
+
+
 def _stream_ptr(stream=None):
     s = torch.cuda.current_stream() if stream is None else stream
     return ctypes.c_void_p(s.cuda_stream)
@@ -61,7 +78,7 @@ def fa_forward(q, k, v, scale=None, out=None, stream=None):
     if out is None:
         out = torch.empty_like(q)
     lib = load_library()
-    with torch.cuda.device(q.device):
+    with _on(q.device):
         dev, shp = q.device, (B, H, N, D)
         check(lib.fa_forward(_dev_ptr(q, torch.float16, "Q"), _dev_ptr(k, torch.float16, "K", shp, dev),
                              _dev_ptr(v, torch.float16, "V", shp, dev), _dev_ptr(out, torch.float16, "O", shp, dev),
@@ -79,7 +96,7 @@ def fa_forward_f32out(q, k, v, scale=None, out=None, stream=None):
     if out is None:
         out = torch.empty((B, H, N, D), dtype=torch.float32, device=q.device)
     lib = load_library()
-    with torch.cuda.device(q.device):
+    with _on(q.device):
         dev, shp = q.device, (B, H, N, D)
         check(lib.fa_forward_f32out(_dev_ptr(q, torch.float16, "Q"), _dev_ptr(k, torch.float16, "K", shp, dev),
                                     _dev_ptr(v, torch.float16, "V", shp, dev), _dev_ptr(out, torch.float32, "O", shp, dev),
@@ -99,7 +116,7 @@ def fa_forward_cross(q, k, v, scale=None, out=None, stream=None):
     if out is None:
         out = torch.empty((B, H, Nq, D), dtype=torch.float32, device=q.device)
     lib = load_library()
-    with torch.cuda.device(q.device):
+    with _on(q.device):
         dev, kshp = q.device, (B, H, Nkv, D)
         check(lib.fa_forward_cross(_dev_ptr(q, torch.float16, "Q"), _dev_ptr(k, torch.float16, "K", kshp, dev),
                                    _dev_ptr(v, torch.float16, "V", kshp, dev),
@@ -117,7 +134,7 @@ def fa_forward_partial(q, k, v, o_acc, m, l, scale, is_first, is_last, o_final=N
     if is_last and o_final is None:
         o_final = torch.empty_like(q)
     lib = load_library()
-    with torch.cuda.device(q.device):
+    with _on(q.device):
         dev, kshp = q.device, (B, H, Nkv, D)
         check(lib.fa_forward_partial(_dev_ptr(q, torch.float16, "Q"), _dev_ptr(k, torch.float16, "K", kshp, dev),
                                      _dev_ptr(v, torch.float16, "V", kshp, dev),
@@ -152,7 +169,7 @@ def gemm_fused_epilogue(a, b, bias=None, residual=None, out=None, stream=None, a
     if residual is not None and tuple(residual.shape) != (M, N):
         raise ValueError("residual must be [M, N]")
     lib = load_library()
-    with torch.cuda.device(a.device):
+    with _on(a.device):
         dev = a.device
         ptrs = (_dev_ptr(a, torch.float16, "A"), _dev_ptr(b, torch.float16, "B", (K, N), dev),
                 _dev_ptr(bias, torch.float32, "bias", (N,), dev),
@@ -180,7 +197,7 @@ def gemm_fused_epilogue_f32(a, b, bias=None, residual=None, out=None, stream=Non
     if out is None:
         out = torch.empty((M, N), dtype=torch.float32, device=a.device)
     lib = load_library()
-    with torch.cuda.device(a.device):
+    with _on(a.device):
         dev = a.device
         check(lib.gemm_fused_epilogue_f32(_dev_ptr(a, torch.float32, "A"), _dev_ptr(b, torch.float32, "B", (K, N), dev),
                                           _dev_ptr(bias, torch.float32, "bias", (N,), dev),
@@ -228,7 +245,7 @@ def gemm_batched(a, b, trans_b=False, alpha=1.0, out=None, stream=None):
     elif tuple(out.shape) != (batch, M, N):
         raise ValueError("C must be [batch, M, N]")
     lib = load_library()
-    with torch.cuda.device(a.device):
+    with _on(a.device):
         if a.is_contiguous() and b.is_contiguous() and out.is_contiguous():
             check(lib.gemm_batched(_dev_ptr(a, torch.float16, "A"), _dev_ptr(b, torch.float16, "B", None, a.device),
                                    _dev_ptr(out, torch.float32, "C", (batch, M, N), a.device), batch, M, N, K,
@@ -251,7 +268,7 @@ def softmax_rows(x, out=None, stream=None):
     if out is None:
         out = torch.empty_like(x)
     lib = load_library()
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         check(lib.softmax_rows(_dev_ptr(x, torch.float32, "X"), _dev_ptr(out, torch.float32, "P", (rows, N), x.device),
                                rows, N, _stream_ptr(stream)), "softmax_rows")
     return out
@@ -266,7 +283,7 @@ def softmax_rows_f16out(x, out=None, stream=None):
     if out is None:
         out = torch.empty((rows, N), dtype=torch.float16, device=x.device)
     lib = load_library()
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         check(lib.softmax_rows_f16out(_dev_ptr(x, torch.float32, "X"),
                                       _dev_ptr(out, torch.float16, "P", (rows, N), x.device), rows, N,
                                       _stream_ptr(stream)), "softmax_rows_f16out")
@@ -291,7 +308,7 @@ def fa_forward_unfused(q, k, v, scale=None, workspace=None, stream=None):
     if tuple(S.shape) != (B * H, N, N) or tuple(P.shape) != (B * H, N, N):
         raise ValueError("workspace must be (fp32 [B*H,N,N], fp16 [B*H,N,N])")
     lib = load_library()
-    with torch.cuda.device(q.device):
+    with _on(q.device):
         check(lib.fa_forward_unfused(_dev_ptr(q, torch.float16, "Q"), _dev_ptr(k, torch.float16, "K"),
                                      _dev_ptr(v, torch.float16, "V"), _dev_ptr(out, torch.float32, "O"),
                                      _dev_ptr(S, torch.float32, "S"), _dev_ptr(P, torch.float16, "P"), B, H, N, D,

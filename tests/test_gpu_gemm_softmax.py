@@ -216,8 +216,10 @@ def test_gemm_rejects_unknown_activation(fa):
 def test_fp32_operand_gemm_parity(fa, oracle, shape):
     """gemm_fused_epilogue_f32 (the reference's gemm_tiled_fused_kernel, GEMM/gemm_fused_epilogue/gemm_fused_epilogue.cu:
     44-111; its harness shape is 1024^3 with mt19937(42) uniform(-1,1)): fp32 operands on the tensor cores as split
-    tf32 pairs.  Against the oracle (fp32, k ascending) the difference is fp32 summation order only; a PLAIN tf32
-    product would be ~4e-3 off at K = 1024 -- the bound below is what proves the split works."""
+    tf32 pairs.  Tolerance: the north-star's max-abs <= 2e-3 and rel-L2 <= 1e-3 against the fp32 CPU reference --
+    measured 4.1e-4 / ~2e-5 at 1024^3, where a PLAIN tf32 product is 1.3e-2 off: the products are fp32-exact, what
+    remains is the tensor core's truncating fp32 accumulation (3 * K / 8 accumulate steps), so the second assertion
+    demands at least 10x less error than tf32-rounded operands would give."""
     M, N, K = shape
     rng = np.random.default_rng(42)
     a, b = rng.uniform(-1, 1, (M, K)).astype(np.float32), rng.uniform(-1, 1, (K, N)).astype(np.float32)
@@ -226,12 +228,15 @@ def test_fp32_operand_gemm_parity(fa, oracle, shape):
     got = fa.gemm_fused_epilogue_f32(ta, tb, tbias, tres)
     torch.cuda.synchronize()
     ref = oracle.gemm_fused(a, b, bias, res)
-    assert oracle.max_abs(got.cpu().numpy(), ref) <= 1e-4 * max(1.0, np.sqrt(K / 1024)) and oracle.rel_l2(got.cpu().numpy(), ref) <= 1e-5
-    # nullable operands and another activation
-    got2 = fa.gemm_fused_epilogue_f32(ta, tb, None, None, act="identity").cpu().numpy()
-    assert oracle.max_abs(got2, a.astype(np.float64) @ b.astype(np.float64)) <= 1e-4 * max(1.0, np.sqrt(K / 1024))
+    assert oracle.max_abs(got.cpu().numpy(), ref) <= 2e-3 and oracle.rel_l2(got.cpu().numpy(), ref) <= 1e-4
+    # nullable operands and another activation; compare with what tf32-rounded operands would give
+    got2 = fa.gemm_fused_epilogue_f32(ta, tb, None, None, act="identity").cpu().numpy().astype(np.float64)
+    exact = a.astype(np.float64) @ b.astype(np.float64)
+    tf32 = lambda x: ((x.view(np.uint32) + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32).astype(np.float64)
+    err_tf32 = np.abs(tf32(a) @ tf32(b) - exact).max()
+    assert np.abs(got2 - exact).max() <= max(err_tf32 / 10, 2e-5), (np.abs(got2 - exact).max(), err_tf32)
     if ref_available("gemm_fp32_fused") and M % 32 == 0:
         theirs = torch.zeros_like(got)
         RefGpu().gemm_fp32_fused(ta, tb, tbias, tres, theirs)
         torch.cuda.synchronize()
-        assert (got - theirs).abs().max().item() <= 1e-4
+        assert (got - theirs).abs().max().item() <= 2e-3
