@@ -327,7 +327,7 @@ template <int D>
 int launch_fa(DeviceState* st, const FaCall& c, cudaStream_t stream) {
   using Cfg = FaCfg<D>;
   const uint64_t BH = static_cast<uint64_t>(c.B) * c.H;
-  CUtensorMap mq, mk, mv, mo;
+  CUtensorMap mq, mk, mv, mo, mo32;
   const uint32_t box[3] = {64, 128, 1};
   const uint64_t dq[3] = {static_cast<uint64_t>(D), static_cast<uint64_t>(c.Nq), BH};
   const uint64_t dk[3] = {static_cast<uint64_t>(D), static_cast<uint64_t>(c.Nkv), BH};
@@ -339,6 +339,12 @@ int launch_fa(DeviceState* st, const FaCall& c, cudaStream_t stream) {
     if ((rc = make_map(&mo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, c.O16, 3, dq, box)) != FA_OK) return rc;
   } else {
     mo = mq;  // never dereferenced in the modes that pass no fp16 output
+  }
+  if (c.O32 != nullptr) {  // fp32 output / carried O_acc: boxes of 32 fp32 columns (one 128-byte swizzle row) x 128 rows
+    const uint32_t box32[3] = {32, 128, 1};
+    if ((rc = make_map(&mo32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, c.O32, 3, dq, box32)) != FA_OK) return rc;
+  } else {
+    mo32 = mq;  // never dereferenced in FA_MODE_F16
   }
   bool* flag = (D == 64) ? &st->attr_fa64 : &st->attr_fa128;
   {
@@ -392,7 +398,7 @@ int launch_fa(DeviceState* st, const FaCall& c, cudaStream_t stream) {
     p.ws = reinterpret_cast<float*>(static_cast<char*>(ws) + count_bytes);
   }
   const unsigned grid = static_cast<unsigned>(plan.items_full + plan.tail_ctas);
-  fa_fwd_kernel<D><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(mq, mk, mv, mo, p);
+  fa_fwd_kernel<D><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(mq, mk, mv, mo, mo32, p);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();
   if (ws != nullptr) {

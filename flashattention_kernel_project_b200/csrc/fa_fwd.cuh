@@ -84,7 +84,7 @@ struct FaCfg {
   static constexpr int kOffSum = kOffFac + 2 * 128 * 4;          // float[2][128] final l
   static constexpr int kOffBar = kOffSum + 2 * 128 * 4;
   static constexpr int kPChunks = 2;                    // P is published in two chunks: keys [0, 16*kSplitGroups), then the rest
-  static constexpr int kNumBars = 2 + 2 * kStages + 8 + 2 * kPChunks + 2;  // + merge_full[2] (stream-K tail)
+  static constexpr int kNumBars = 2 + 2 * kStages + 8 + 2 * kPChunks + 4;  // + merge_full[2] (stream-K tail), acc_full[2]
   static constexpr int kOffTmem = kOffBar + kNumBars * 8;
   static constexpr int kSmemBytes = kOffTmem + 16;
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
@@ -93,7 +93,7 @@ struct FaCfg {
 // mbarrier wait sites (reported through the debug channel on a timeout)
 enum : uint32_t {
   SITE_TMA_EMPTY = 1, SITE_MMA_QFULL, SITE_MMA_KVFULL, SITE_MMA_PFULL,
-  SITE_SM_SFULL, SITE_SM_CORR, SITE_CO_STATS, SITE_CO_LFULL, SITE_CO_OFULL, SITE_CO_MERGE
+  SITE_SM_SFULL, SITE_SM_CORR, SITE_CO_STATS, SITE_CO_LFULL, SITE_CO_OFULL, SITE_CO_MERGE, SITE_CO_ACC
 };
 
 constexpr float kLazyRescaleTau = 8.0f;  // log2 units: P stays below 2^8, far inside fp16 range
@@ -185,7 +185,7 @@ __host__ __device__ __forceinline__ bool fa_segment(const FaParams& p, int nkv_t
 }
 
 // (Re-)arms every mbarrier of the CTA; one thread, between two CTA-wide barriers.  Layout as in the kernel:
-// q_full[2], kv_full[S], kv_empty[S], s_full[2], p_full[2][chunks], stats_full[2], o_full[2], l_full[2], merge_full[2].
+// q_full[2], kv_full[S], kv_empty[S], s_full[2], p_full[2][chunks], stats_full[2], o_full[2], l_full[2], merge_full[2], acc_full[2].
 template <int D>
 __device__ __forceinline__ void fa_init_barriers(uint64_t* bars, bool reinit) {
   using Cfg = FaCfg<D>;
@@ -201,6 +201,7 @@ __device__ __forceinline__ void fa_init_barriers(uint64_t* bars, bool reinit) {
   for (int i = 0; i < 2; ++i) mbar_init(b++, 1);  // o_full
   for (int i = 0; i < 2; ++i) mbar_init(b++, 4);  // l_full
   for (int i = 0; i < 2; ++i) mbar_init(b++, 1);  // merge_full
+  for (int i = 0; i < 2; ++i) mbar_init(b++, 1);  // acc_full
   fence_mbar_init();
 }
 // Between two segments of a tail CTA: every role has finished the previous segment (the epilogue's TMA store has read
@@ -218,7 +219,7 @@ template <int D>
 __global__ void __launch_bounds__(512, 1)
 fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
               const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapO,
-              const FaParams p) {
+              const __grid_constant__ CUtensorMap mapO32, const FaParams p) {
   using Cfg = FaCfg<D>;
   extern __shared__ __align__(1024) uint8_t smem[];
 
@@ -236,6 +237,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
   uint64_t* const o_full = stats_full + 2;                // [2]  MMA -> correction : last PV done
   uint64_t* const l_full = o_full + 2;                    // [2]  softmax -> correction : final l
   uint64_t* const merge_full = l_full + 2;                // [2]  bulk copy -> correction : a parked part landed (tail merge)
+  uint64_t* const acc_full = merge_full + 2;              // [2]  TMA -> correction : carried fp32 O_acc tile landed (STATE mode)
   uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(smem + Cfg::kOffTmem);  // [0] TMEM base, [1] merge verdict
 
   const int warp = threadIdx.x >> 5;
@@ -257,6 +259,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
     prefetch_tensormap(&mapK);
     prefetch_tensormap(&mapV);
     if (p.mode != FA_MODE_F32 && !(p.mode == FA_MODE_STATE && !p.is_last)) prefetch_tensormap(&mapO);
+    if (p.mode != FA_MODE_F16) prefetch_tensormap(&mapO32);
   }
   if (warp == 8) {
     tmem_alloc(tmem_slot, Cfg::kTmemCols);
@@ -600,6 +603,31 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
       }
 
       // ---- epilogue: O / l -> output ----
+      // fp16 output leaves through the (dead) Q tiles and a TMA store.  fp32 traffic -- the fp32 output of
+      // fa_forward_f32out / _cross and the carried O_acc of a ring step, read AND written -- goes through TMA as well,
+      // staged in the K/V ring, which is idle once the last PV of the last tile has completed: a lane owns a whole
+      // accumulator row (tcgen05.ld 32x32b), the worst shape for global memory (512-byte stride between lanes), and
+      // row-per-thread float4 loads / stores cost a ring step of BASELINE config 4 at 8 GPUs 15 % of its time.
+      const bool f32_traffic = (p.mode != FA_MODE_F16);
+      const bool have_acc = (p.mode == FA_MODE_STATE) && !p.is_first;
+      constexpr int kTileF32Bytes = D * 128 * 4, kBoxF32Bytes = 128 * 128;  // boxes of 32 fp32 columns x 128 rows
+      if (f32_traffic) {
+        mbar_wait(&o_full[ntile - 1], 0, dbg, SITE_CO_OFULL, ntile - 1);  // nothing reads the ring any more
+        if (have_acc && warp == 8) {
+          const int bh_u = __shfl_sync(0xffffffffu, bh, 0), q0_u = __shfl_sync(0xffffffffu, q0, 0);
+          const int nt_u = __shfl_sync(0xffffffffu, ntile, 0);
+          if (elect_one()) {
+            for (int i = 0; i < nt_u; ++i) {
+              mbar_arrive_expect_tx(&acc_full[i], kTileF32Bytes);
+#pragma unroll
+              for (int bx = 0; bx < D / 32; ++bx)
+                tma_load_3d(kv_smem + i * kTileF32Bytes + bx * kBoxF32Bytes, &mapO32, &acc_full[i], bx * 32, q0_u + i * 128,
+                            bh_u, kEvictFirst);  // rows >= nq arrive as zeros
+            }
+          }
+          __syncwarp();
+        }
+      }
       for (int i = 0; i < ntile; ++i) {
         mbar_wait(&l_full[i], 0, dbg, SITE_CO_LFULL, i);
         mbar_wait(&o_full[i], 0, dbg, SITE_CO_OFULL, i);
@@ -612,8 +640,6 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
         float o_scale = 1.f;      // factor applied to this step's un-normalised O
         float acc_scale = 0.f;    // factor applied to the carried O_acc (STATE mode)
         bool emit_f16 = (p.mode == FA_MODE_F16);
-        bool emit_f32 = (p.mode == FA_MODE_F32);
-        bool emit_state = false;
         const size_t row_index = static_cast<size_t>(bh) * p.nq + grow;
         if (p.mode == FA_MODE_STATE) {
           // Merge (O, m, l) of this K/V shard into the carried state: the reference's tile-to-tile
@@ -633,19 +659,16 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
             const float inv = 1.f / l_tot;
             o_scale *= inv;
             acc_scale *= inv;
-          } else {
-            emit_state = true;
-            if (row_ok) {
-              p.m_state[row_index] = m_tot;
-              p.l_state[row_index] = l_tot;
-            }
+          } else if (row_ok) {
+            p.m_state[row_index] = m_tot;
+            p.l_state[row_index] = l_tot;
           }
         } else {
           o_scale = 1.f / l_new;
         }
-        const bool have_acc = (p.mode == FA_MODE_STATE) && !p.is_first;
-        float* const acc_row = p.o_f32 + row_index * D;
-        uint8_t* const stage = q_smem + i * Cfg::kTileBytes;  // Q tile i is dead once o_full fired
+        uint8_t* const stage = q_smem + i * Cfg::kTileBytes;           // fp16: Q tile i is dead once o_full fired
+        uint8_t* const stage32 = kv_smem + i * kTileF32Bytes;          // fp32: the idle K/V ring
+        if (have_acc) mbar_wait(&acc_full[i], 0, dbg, SITE_CO_ACC, i);
 
 #pragma unroll
         for (int cc = 0; cc < D / 32; ++cc) {
@@ -655,18 +678,20 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
           float v[32];
 #pragma unroll
           for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(o[k]) * o_scale;
-          if (have_acc && row_ok) {
+          // this row's 32 columns inside a 128B-swizzled box of 32 fp32 columns: eight 16-byte chunks, chunk q at q ^ (row & 7)
+          uint8_t* const row32 = stage32 + cc * kBoxF32Bytes + row * 128;
+          if (have_acc) {
 #pragma unroll
-            for (int k = 0; k < 32; k += 4) {
-              const float4 a = *reinterpret_cast<const float4*>(acc_row + cc * 32 + k);
-              v[k + 0] = fmaf(a.x, acc_scale, v[k + 0]);
-              v[k + 1] = fmaf(a.y, acc_scale, v[k + 1]);
-              v[k + 2] = fmaf(a.z, acc_scale, v[k + 2]);
-              v[k + 3] = fmaf(a.w, acc_scale, v[k + 3]);
+            for (int q = 0; q < 8; ++q) {
+              const float4 a = *reinterpret_cast<const float4*>(row32 + ((q ^ (row & 7)) << 4));
+              v[4 * q + 0] = fmaf(a.x, acc_scale, v[4 * q + 0]);
+              v[4 * q + 1] = fmaf(a.y, acc_scale, v[4 * q + 1]);
+              v[4 * q + 2] = fmaf(a.z, acc_scale, v[4 * q + 2]);
+              v[4 * q + 3] = fmaf(a.w, acc_scale, v[4 * q + 3]);
             }
           }
           if (emit_f16) {
-            // 32 columns = 64 B = four 16-byte chunks of this row inside a 128B-swizzled box
+            // 32 columns = 64 B = four 16-byte chunks of this row inside a 128B-swizzled box of 64 fp16 columns
             uint8_t* const box = stage + (cc >> 1) * Cfg::kBoxBytes + row * 128;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -678,26 +703,31 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
               const int chunk = (cc & 1) * 4 + q;
               *reinterpret_cast<uint4*>(box + ((chunk ^ (row & 7)) << 4)) = w;
             }
-          } else if ((emit_f32 || emit_state) && row_ok) {
+          } else {
 #pragma unroll
-            for (int k = 0; k < 32; k += 4)
-              *reinterpret_cast<float4*>(acc_row + cc * 32 + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<float4*>(row32 + ((q ^ (row & 7)) << 4)) =
+                  make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
           }
         }
-        if (emit_f16) {
-          fence_proxy_async_smem();
-          named_bar_sync(1, 128);
-          if (warp == 8) {
-            // warp-uniform coordinates (a shuffle from lane 0 is what lets ptxas issue the TMA store without a
-            // per-thread serialisation loop); lane 0 owns the bulk group it later waits on
-            const int row0 = __shfl_sync(0xffffffffu, q0 + i * 128, 0), bh_u = __shfl_sync(0xffffffffu, bh, 0);
-            const uint8_t* const stage_u = q_smem + __shfl_sync(0xffffffffu, i, 0) * Cfg::kTileBytes;
-            if (lane == 0) {
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (warp == 8) {
+          // warp-uniform coordinates (a shuffle from lane 0 is what lets ptxas issue the TMA store without a
+          // per-thread serialisation loop); lane 0 owns the bulk group it later waits on
+          const int row0 = __shfl_sync(0xffffffffu, q0 + i * 128, 0), bh_u = __shfl_sync(0xffffffffu, bh, 0);
+          const int i_u = __shfl_sync(0xffffffffu, i, 0);
+          if (lane == 0) {
+            if (emit_f16) {
 #pragma unroll
               for (int b = 0; b < Cfg::kBoxes; ++b)
-                tma_store_3d(&mapO, stage_u + b * Cfg::kBoxBytes, b * 64, row0, bh_u);  // clips rows >= nq
-              tma_store_commit();
+                tma_store_3d(&mapO, q_smem + i_u * Cfg::kTileBytes + b * Cfg::kBoxBytes, b * 64, row0, bh_u);  // clips rows >= nq
+            } else {
+#pragma unroll
+              for (int b = 0; b < D / 32; ++b)
+                tma_store_3d(&mapO32, kv_smem + i_u * kTileF32Bytes + b * kBoxF32Bytes, b * 32, row0, bh_u);
             }
+            tma_store_commit();
           }
         }
       }

@@ -81,11 +81,19 @@ def test_kernels_keep_their_state_in_registers():
 
 def test_attention_hot_roles_do_not_spill(sass):
     """The roles are laid out in program order softmax (after the setmaxnreg.inc), correction (first dealloc), MMA,
-    TMA: local-memory traffic is allowed only between the first and the second USETMAXREG.DEALLOC, i.e. in the
-    correction warps (see above)."""
+    prefetch, TMA.  The softmax role touches no local memory at all; nothing after the correction role ever STORES
+    to local memory (so the MMA / TMA / prefetch roles spill nothing), and the only local loads found there are cold
+    blocks of the correction role that ptxas placed at the end of the function (they reload slots stored by it)."""
+    import re
     for body in _one(sass, "fa_fwd_kernel"):
         lines = body.splitlines()
         marks = [i for i, l in enumerate(lines) if "USETMAXREG" in l]
         assert len(marks) >= 4 and "TRY_ALLOC" in lines[marks[0]]
-        spills = [i for i, l in enumerate(lines) if " STL" in l or " LDL" in l]
-        assert all(marks[1] < i < marks[2] for i in spills), "a hot role touches local memory"
+        is_st = lambda l: re.search(r"\bSTL(\.|\s)", l) is not None
+        is_ld = lambda l: re.search(r"\bLDL(\.|\s)", l) is not None
+        assert not any(is_st(l) or is_ld(l) for l in lines[marks[0]:marks[1]]), "the softmax role touches local memory"
+        assert not any(is_st(l) for l in lines[marks[2]:]), "a role after the correction warps spills"
+        slot = lambda l: re.search(r"\[R1(\+0x[0-9a-f]+)?\]", l).group(0)
+        stored = {slot(l) for l in lines[marks[1]:marks[2]] if is_st(l)}
+        late = {slot(l) for l in lines[marks[2]:] if is_ld(l)}
+        assert late <= stored, (late, stored)
