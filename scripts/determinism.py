@@ -22,7 +22,7 @@ if diff.any():
 s = fa.fa_forward(q[:1, :2].contiguous(), k[:1, :2].contiguous(), v[:1, :2].contiguous(), sc)
 torch.cuda.synchronize()
 d2 = (s != a[:1, :2])
-print("slice vs full: mismatching", int(d2.sum()), "of", s.numel())
+print("slice vs full (the slice is cut along K/V, the batch is not: fa_plan): mismatching", int(d2.sum()), "of", s.numel())
 if d2.any():
     idx = d2.nonzero()
     print(" first:", idx[:10].tolist(), "max abs", (s.float() - a[:1, :2].float()).abs().max().item())
@@ -30,8 +30,9 @@ if d2.any():
     print(" rows affected:", rows.shape[0], "cols hist(32-col chunks):", torch.bincount(idx[:, 3] // 32, minlength=4).tolist())
 s2 = fa.fa_forward(q[:1, :2].contiguous(), k[:1, :2].contiguous(), (v[:1, :2] * 2).contiguous(), sc)
 torch.cuda.synchronize()
-d3 = (s2.float() != s.float() * 2)
-print("2V vs 2*O (slice): mismatching", int(d3.sum()))
+# outputs below 2^-13 are fp16 subnormals before or after doubling: excluded, as in tests/test_gpu_attention.py
+d3 = (s2.float() != s.float() * 2) & (s.float().abs() >= 2.0 ** -13)
+print("2V vs 2*O (slice, fp16-normal outputs): mismatching", int(d3.sum()))
 if d3.any():
     idx = d3.nonzero()
     print(" first:", idx[:10].tolist())
