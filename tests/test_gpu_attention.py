@@ -193,6 +193,31 @@ def test_cut_items_match_whole_items(fa, oracle):
         _check(oracle, cut32.cpu().numpy().reshape(B * H, N, D), ref, rel_tol=5e-4)
 
 
+def test_cut_is_deterministic_under_concurrency(fa):
+    """The merge of a cut item is done by whichever CTA arrives last; it reduces the parts in span order, so the result
+    must not depend on which one that is: repeated launches, overlapping on two streams (each launch owns its
+    stream-ordered workspace), are bit-identical (scripts/stress_cut.py is the long version)."""
+    lib = fa.load_library()
+    before = lib.fa_set_tail_split(2)
+    side = torch.cuda.Stream()
+    try:
+        for (B, H, N, D) in [(1, 40, 2048, 128), (1, 5, 2304, 64)]:
+            q, k, v = (torch.from_numpy(x).cuda() for x in _inputs(B, H, N, D, dist="normal", seed=B + N))
+            first, first32 = fa.fa_forward(q, k, v, 0.1), fa.fa_forward_f32out(q, k, v, 0.1)
+            torch.cuda.synchronize()
+            for _ in range(8):
+                a = fa.fa_forward(q, k, v, 0.1)
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    b = fa.fa_forward_f32out(q, k, v, 0.1)
+                c = fa.fa_forward(q, k, v, 0.1)
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                assert torch.equal(a, first) and torch.equal(c, first) and torch.equal(b, first32)
+    finally:
+        lib.fa_set_tail_split(before)
+
+
 def test_deterministic_and_stream_ordered(fa):
     B, H, N, D = 2, 4, 777, 128
     q, k, v = (torch.from_numpy(x).cuda() for x in _inputs(B, H, N, D, seed=9))
