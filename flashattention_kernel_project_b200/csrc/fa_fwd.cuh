@@ -628,9 +628,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
           __syncwarp();
         }
       }
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {  // unrolled: the tile index is a constant in every TMA address below
-        if (i >= ntile) break;
+      for (int i = 0; i < ntile; ++i) {
         mbar_wait(&l_full[i], 0, dbg, SITE_CO_LFULL, i);
         mbar_wait(&o_full[i], 0, dbg, SITE_CO_OFULL, i);
         tc_fence_after();
@@ -718,15 +716,16 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
           // warp-uniform coordinates (a shuffle from lane 0 is what lets ptxas issue the TMA store without a
           // per-thread serialisation loop); lane 0 owns the bulk group it later waits on
           const int row0 = __shfl_sync(0xffffffffu, q0 + i * 128, 0), bh_u = __shfl_sync(0xffffffffu, bh, 0);
+          const int i_u = __shfl_sync(0xffffffffu, i, 0);
           if (lane == 0) {
             if (emit_f16) {
 #pragma unroll
               for (int b = 0; b < Cfg::kBoxes; ++b)
-                tma_store_3d(&mapO, q_smem + i * Cfg::kTileBytes + b * Cfg::kBoxBytes, b * 64, row0, bh_u);  // clips rows >= nq
+                tma_store_3d(&mapO, q_smem + i_u * Cfg::kTileBytes + b * Cfg::kBoxBytes, b * 64, row0, bh_u);  // clips rows >= nq
             } else {
 #pragma unroll
               for (int b = 0; b < D / 32; ++b)
-                tma_store_3d(&mapO32, kv_smem + i * kTileF32Bytes + b * kBoxF32Bytes, b * 32, row0, bh_u);
+                tma_store_3d(&mapO32, kv_smem + i_u * kTileF32Bytes + b * kBoxF32Bytes, b * 32, row0, bh_u);
             }
             tma_store_commit();
           }
