@@ -244,7 +244,10 @@ def ring_cfg4(torch, dist, fa, dev, rank, world):
     q, k, v = ((torch.rand((B, H, n, D), device=dev, generator=g) * 2 - 1).half() for _ in range(3))
     out = torch.empty_like(q)
     ws = fa.RingWorkspace(q.shape, world, dev)
-    peers = fa.PeerShards(k, v)
+    try:  # CUDA IPC needs plain cudaMalloc memory (the default torch allocator); the same outcome on every rank
+        peers, peers_error = fa.PeerShards(k, v), None
+    except Exception as e:  # noqa: BLE001
+        peers, peers_error = None, f"{type(e).__name__}: {e}"[:200]
 
     def timed(fn, iters):
         dist.barrier()
@@ -255,8 +258,9 @@ def ring_cfg4(torch, dist, fa, dev, rank, world):
         return float(t.item())
     # two exchanges, same arithmetic (bit-identical results): grouped ncclSend/ncclRecv on a side stream, and the
     # exchange fused into the attention kernel (its spare warps load the next shard from the owner over NVLink)
-    variants = {"nccl": lambda: fa.ring_forward(q, k, v, scale, out=out, workspace=ws),
-                "fused_peer_loads": lambda: fa.ring_forward(q, k, v, scale, out=out, workspace=ws, peers=peers)}
+    variants = {"nccl": lambda: fa.ring_forward(q, k, v, scale, out=out, workspace=ws)}
+    if peers is not None:
+        variants["fused_peer_loads"] = lambda: fa.ring_forward(q, k, v, scale, out=out, workspace=ws, peers=peers)
     ms_by = {}
     for name, fn in variants.items():
         for _ in range(2):
@@ -297,7 +301,8 @@ def ring_cfg4(torch, dist, fa, dev, rank, world):
         ms_1 = time_loop(torch, one, 2) / 2
         del qf, kf, vf, o1
     dist.barrier()
-    peers.close()
+    if peers is not None:
+        peers.close()
     if rank != 0:
         return None
     from tests.oracle_lib import Oracle
@@ -315,7 +320,7 @@ def ring_cfg4(torch, dist, fa, dev, rank, world):
                             "high-priority stream, enqueued from C++",
                     "fused_peer_loads": "fa_ring_forward_pull (C ABI): one launch per step, the kernel's two spare warps "
                                         "per CTA load the next K/V shard from its owner's memory (CUDA IPC peer mapping)"},
-            "exchange": best, "ms_by_exchange": ms_by,
+            "exchange": best, "ms_by_exchange": ms_by, "peer_mapping_error": peers_error,
             "n_gpus": world, "ms": ms, "tflops_total": fl / ms / 1e9, "ms_compute_only": ms_c,
             "exchange_overhead": ms / ms_c - 1.0, "ms_1gpu": ms_1, "speedup_vs_1gpu": ms_1 / ms,
             "exchange_bytes_per_gpu": 2 * (world - 1) * B * H * n * D * 2,
