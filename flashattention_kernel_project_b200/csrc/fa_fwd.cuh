@@ -17,13 +17,18 @@
 //                 tcgen05.ld 32x32b gives each thread one whole row: no shuffles at all
 //   rescale     : O_smem *= alpha every tile (v5:352-360) -> only when the running max grows by
 //                 more than 2^8 (lazy), done by a dedicated correction warpgroup on TMEM
-//   epilogue    : scalar fp32 stores (v4:403-412) -> 1/l in registers, fp16, swizzled smem, TMA store
+//   epilogue    : scalar fp32 stores (v4:403-412) -> 1/l in registers, fp16, swizzled smem, TMA store; fp32 output
+//                 and the carried (O_acc) state of a ring step: TMA as well, staged in the idle K/V ring
+//   grid        : one CTA per (query block, b*h) (v4:452) -> the same by default; grids that fill less than half the
+//                 SMs are cut along K/V into equal spans whose parts are merged by the last CTA to arrive (FaSegment)
 //
 // CTA = 512 threads = 4 warpgroups, one CTA per SM, 256 query rows per CTA as two 128-row tiles
 // that ping-pong on the tensor pipe:
 //   WG0 (warps 0-3)   softmax of Q tile 0        WG1 (warps 4-7)  softmax of Q tile 1
 //   WG2 (warps 8-11)  correction + epilogue      WG3: warp 12 = MMA issuer (one elected lane),
-//                                                     warp 13 = TMA producer
+//                                                     warp 13 = TMA producer,
+//                                                     warps 14-15 = spare; in a ring step they pull the NEXT
+//                                                     step's K / V shard from its owner GPU (peer loads)
 // TMEM (512 columns x 128 lanes x 32 bit): S0 @0, S1 @128, O0 @256, O1 @256+D.  P (fp16, two per
 // column) overwrites the first 64 columns of its own S.
 #pragma once
