@@ -126,3 +126,47 @@ def test_plain_c_program_through_the_c_abi(tmp_path):
     r = build_and_run_c_example(tmp_path)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "max abs error" in r.stdout
+
+
+@pytest.mark.parametrize("world,shape", [(2, (1, 4, 1024, 128)), (4, (2, 3, 1024, 64)), (8, (1, 2, 4096, 128)), (3, (1, 2, 768, 64))])
+def test_fused_ring_with_every_rank_driven_on_one_gpu(fa, oracle, world, shape):
+    """fa_ring_forward_pull on ONE GPU: every rank's call is made in turn by this process, the "peer" pointers being the
+    other ranks' shards on the same device (the header allows plain pointers when one process drives several GPUs;
+    a call never waits for another rank).  This runs the complete product path of the context-parallel ring -- P
+    launches per rank, the spare warps of every CTA loading the next step's K / V shard, the carried fp32 state through
+    TMA, two alternating receive buffers -- where only one GPU is available, against the oracle on the whole sequence."""
+    import ctypes
+    B, H, N, D = shape
+    n = N // world
+    q, k, v = _inputs(B, H, N, D, seed=world + N, std=1.2)
+    scale = 1.0 / np.sqrt(D)
+    lib = fa.load_library()
+    shards = lambda x: [torch.from_numpy(np.ascontiguousarray(x[:, :, r * n:(r + 1) * n])).cuda() for r in range(world)]
+    qs, ks, vs = shards(q), shards(k), shards(v)
+    nbytes = int(lib.fa_ring_workspace_bytes(B, H, n, D, world, 2))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    peer_k = (ctypes.c_void_p * world)(*[ctypes.c_void_p(t.data_ptr()) for t in ks])
+    peer_v = (ctypes.c_void_p * world)(*[ctypes.c_void_p(t.data_ptr()) for t in vs])
+    outs = []
+    for r in range(world):
+        out = torch.empty_like(qs[r])
+        ws.fill_(0xFF)  # stale workspace contents (NaN patterns) must not leak into the result
+        rc = lib.fa_ring_forward_pull(ctypes.c_void_p(qs[r].data_ptr()), ctypes.c_void_p(ks[r].data_ptr()),
+                                      ctypes.c_void_p(vs[r].data_ptr()), ctypes.c_void_p(out.data_ptr()), B, H, n, D,
+                                      ctypes.c_float(scale), r, world, peer_k, peer_v, ctypes.c_void_p(ws.data_ptr()),
+                                      ctypes.c_size_t(nbytes), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0, rc
+        outs.append(out)
+    torch.cuda.synchronize()
+    got = torch.cat(outs, dim=2).float().cpu().numpy().reshape(B * H, N, D)
+    ref = oracle.attention_f16(q.reshape(B * H, N, D), k.reshape(B * H, N, D), v.reshape(B * H, N, D), scale)
+    assert oracle.rel_l2(got, ref) <= 1e-3 and oracle.max_abs(got, ref) <= 2e-3 * max(1.0, float(np.abs(ref).max()))
+    # the same steps through fa_forward_partial, no prefetch: bit-identical (same kernel calls, same shard order)
+    r = world - 1
+    o_acc = torch.empty((B, H, n, D), device="cuda")
+    m, l = torch.empty((B, H, n), device="cuda"), torch.empty((B, H, n), device="cuda")
+    for x in range(world):
+        src = (r - x) % world
+        plain = fa.fa_forward_partial(qs[r], ks[src], vs[src], o_acc, m, l, scale, x == 0, x == world - 1)
+    torch.cuda.synchronize()
+    assert torch.equal(plain, outs[r])
