@@ -686,7 +686,9 @@ def extras(torch, fa, dev, peaks):
         f()
     ms = time_loop(torch, f, 50) / 50
     gbs = 2.0 * x.numel() * 4 / ms / 1e6
-    out["softmax_16384x4096"] = {"us": ms * 1e3, "gbs": gbs, "frac_of_measured_hbm": gbs / peaks["hbm_gbs"]}
+    gus = graph_time_us(torch, f, calls=10)
+    out["softmax_16384x4096"] = {"us": ms * 1e3, "gbs": gbs, "frac_of_measured_hbm": gbs / peaks["hbm_gbs"],
+                                 "cuda_graph_us": gus, "cuda_graph_gbs": 2.0 * x.numel() * 4 / gus / 1e3}
     del x, p
     # config 4 on one GPU: B=1,H=32,N=65536,D=128 (70.4 TFLOP per launch)
     B, H, N, D = 1, 32, 65536, 128
