@@ -277,8 +277,11 @@ gemm_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       constexpr uint32_t idesc = kSplit ? umma_idesc_tf32(256, Cfg::kBN) : umma_idesc_f16(256, Cfg::kBN, 0, kTransB ? 0 : 1);
       int it = 0, local = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs, ++local) {
-        const int acc = local & 1;
-        const int acc_par = (local >> 1) & 1;
+        // fp16: two accumulators alternate (the epilogue of tile t overlaps the mainloop of t + 1).  Split fp32: ONE
+        // accumulator pair -- columns [0,256) for A_hi*B_hi, [256,512) for the two small cross terms, so that the
+        // truncating fp32 accumulation of the tensor core sees K/8 steps on the large sum instead of 3K/8
+        const int acc = kSplit ? 0 : (local & 1);
+        const int acc_par = kSplit ? (local & 1) : ((local >> 1) & 1);
         mbar_wait(&tempty[acc], acc_par ^ 1, dbg, SITE_G_TEMPTY, local);
         tc_fence_after();
         const uint32_t d = tmem_base + acc * Cfg::kBN;
@@ -298,8 +301,9 @@ gemm_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
               for (int pass = 0; pass < 3; ++pass)
 #pragma unroll
                 for (int ks = 0; ks < Cfg::kBK / Cfg::kKPerMma; ++ks)
-                  umma_ss_2sm_tf32(d, umma_desc_sw128(pa[pass] + ks * 32, 16, 1024),
-                                   umma_desc_sw128(pb[pass] + ks * 32, 16, 1024), idesc, (kb | ks | pass) ? 1u : 0u);
+                  umma_ss_2sm_tf32(pass < 2 ? d + Cfg::kBN : d, umma_desc_sw128(pa[pass] + ks * 32, 16, 1024),
+                                   umma_desc_sw128(pb[pass] + ks * 32, 16, 1024), idesc,
+                                   pass < 2 ? ((kb | ks | pass) ? 1u : 0u) : ((kb | ks) ? 1u : 0u));
             } else {
 #pragma unroll
               for (int ks = 0; ks < Cfg::kBK / Cfg::kKPerMma; ++ks) {
@@ -345,8 +349,8 @@ gemm_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++local) {
       int bz, mb, nb;
       gemm_tile_coords(tile, p, bz, mb, nb);
-      const int acc = local & 1;
-      const int acc_par = (local >> 1) & 1;
+      const int acc = kSplit ? 0 : (local & 1);
+      const int acc_par = kSplit ? (local & 1) : ((local >> 1) & 1);
       mbar_wait(&tfull[acc], acc_par, dbg, SITE_G_TFULL, local);
       tc_fence_after();
 #pragma unroll 1
@@ -354,6 +358,8 @@ gemm_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         const int b = g % Cfg::kEpiBufs;
         uint32_t r[32];
         tmem_ld_x32(tmem_base + lane_base + acc * Cfg::kBN + cc * Cfg::kEpiCols, r);
+        uint32_t r2[kSplit ? 32 : 1];
+        if constexpr (kSplit) tmem_ld_x32(tmem_base + lane_base + Cfg::kBN + cc * Cfg::kEpiCols, r2);  // the cross terms
         if (has_res) mbar_wait(&rfull[b], (g / Cfg::kEpiBufs) & 1, dbg, SITE_G_RFULL, g);
         tmem_wait_ld();
         if (cc == Cfg::kChunksPerTile - 1) {  // accumulator drained into registers: hand it back to the MMA warp
@@ -365,6 +371,11 @@ gemm_fused_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         const int col0 = nb * Cfg::kBN + cc * Cfg::kEpiCols;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
+          if constexpr (kSplit) {  // large sum + the two small cross terms, rounded to nearest once
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              r[4 * q + e] = __float_as_uint(__uint_as_float(r[4 * q + e]) + __uint_as_float(r2[4 * q + e]));
+          }
           float4 v = make_float4(__uint_as_float(r[4 * q]) * p.alpha, __uint_as_float(r[4 * q + 1]) * p.alpha,
                                  __uint_as_float(r[4 * q + 2]) * p.alpha, __uint_as_float(r[4 * q + 3]) * p.alpha);
           const int col = col0 + q * 4;

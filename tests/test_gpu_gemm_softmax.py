@@ -217,9 +217,9 @@ def test_fp32_operand_gemm_parity(fa, oracle, shape):
     """gemm_fused_epilogue_f32 (the reference's gemm_tiled_fused_kernel, GEMM/gemm_fused_epilogue/gemm_fused_epilogue.cu:
     44-111; its harness shape is 1024^3 with mt19937(42) uniform(-1,1)): fp32 operands on the tensor cores as split
     tf32 pairs.  Tolerance: the north-star's max-abs <= 2e-3 and rel-L2 <= 1e-3 against the fp32 CPU reference --
-    measured 4.1e-4 / ~2e-5 at 1024^3, where a PLAIN tf32 product is 1.3e-2 off: the products are fp32-exact, what
-    remains is the tensor core's truncating fp32 accumulation (3 * K / 8 accumulate steps), so the second assertion
-    demands at least 10x less error than tf32-rounded operands would give."""
+    measured 1.4e-4 at 1024^3, where a PLAIN tf32 product is 1.3e-2 off: the products are fp32-exact, what remains is
+    the tensor core's truncating fp32 accumulation (K / 8 accumulate steps on the large term; the cross terms have
+    their own accumulator), so the second assertion demands at least 10x less error than tf32-rounded operands give."""
     M, N, K = shape
     rng = np.random.default_rng(42)
     a, b = rng.uniform(-1, 1, (M, K)).astype(np.float32), rng.uniform(-1, 1, (K, N)).astype(np.float32)
@@ -228,7 +228,7 @@ def test_fp32_operand_gemm_parity(fa, oracle, shape):
     got = fa.gemm_fused_epilogue_f32(ta, tb, tbias, tres)
     torch.cuda.synchronize()
     ref = oracle.gemm_fused(a, b, bias, res)
-    assert oracle.max_abs(got.cpu().numpy(), ref) <= 2e-3 and oracle.rel_l2(got.cpu().numpy(), ref) <= 1e-4
+    assert oracle.max_abs(got.cpu().numpy(), ref) <= 1e-3 and oracle.rel_l2(got.cpu().numpy(), ref) <= 5e-5
     # nullable operands and another activation; compare with what tf32-rounded operands would give
     got2 = fa.gemm_fused_epilogue_f32(ta, tb, None, None, act="identity").cpu().numpy().astype(np.float64)
     exact = a.astype(np.float64) @ b.astype(np.float64)
