@@ -269,18 +269,25 @@ struct FaCall {
 // So only sub-half-wave grids are cut, into p parts per item with p ~ sqrt(L / 2.2) minimising L/p + 2.2 p
 // (L = key tiles per item), 2 <= p <= min(8, SMs / items), spans of at least 4 key tiles, and only if the model
 // says the cut wins.  FA_TAIL_COST (default 3) is the fixed cost of a cut span in key-tile iterations.
+// The other cut is along QUERY ROWS: an item of a last wave that fills at most half the SMs becomes two CTAs with one
+// 128-row tile each.  Nothing is merged and every row is computed exactly as in the whole item (bit-identical
+// output); a single-tile CTA runs 2761 cycles per key tile against 3234 for two tiles, so the wave ends ~15 % sooner:
+// 32 items of 8 key tiles (B=1,H=8,N=1024,D=64) 16.5 -> 13.7 us, 16 items of 32 key tiles 53.6 -> 49.0 us (K/V cut:
+// 44.6), 512 items (config 3 on 8 GPUs) 233.5 -> 232.3 us.
 struct FaPlan {
   int items_full, tail_items, tail_ctas;
+  int tail_rows;  // the tail is cut along query rows (two single-tile CTAs per item), not along K/V
 };
-// -1: the environment decides (FA_TAIL_SPLIT = 0 / 1 / 2, default 1); 0: never cut; 1: cut where the model above says
-// it pays; 2: cut the partial last wave of ANY grid into equal spans, whatever the model says (the general stream-K
-// plan -- CTAs whose span straddles two items, items shared by up to 8 CTAs; used by the tests and the A/B script)
+// -1: the environment decides (FA_TAIL_SPLIT = 0 ... 3, default 1); 0: never cut; 1: cut where the model above says
+// it pays; 2: cut the partial last wave of ANY grid along K/V into equal spans, whatever the model says (the general
+// stream-K plan -- CTAs whose span straddles two items, items shared by up to 8 CTAs); 3: only the row cut.  2 and 3
+// are for the tests and the A/B script.
 std::atomic<int> g_tail_split{-1};
 int tail_split_mode() {
   static const int env_mode = [] {
     const char* e = std::getenv("FA_TAIL_SPLIT");
     const int v = e == nullptr ? 1 : std::atoi(e);
-    return v < 0 || v > 2 ? 1 : v;
+    return v < 0 || v > 3 ? 1 : v;
   }();
   const int v = g_tail_split.load(std::memory_order_relaxed);
   return v < 0 ? env_mode : v;
@@ -292,12 +299,25 @@ int tail_split_cost() {
   }();
   return cost;
 }
-FaPlan fa_plan(long long items, int nkv_tiles, int sms, bool have_pool) {
-  FaPlan plan{static_cast<int>(items), 0, 0};
+FaPlan fa_plan(long long items, int nkv_tiles, int nq, int sms, bool have_pool) {
+  FaPlan plan{static_cast<int>(items), 0, 0, 0};
   const int mode = tail_split_mode();
-  if (!have_pool || mode == 0 || sms <= 0) return plan;
+  if (mode == 0 || sms <= 0) return plan;
+  const long long rest = items % sms;
+  // Row cut: the items of a last wave that fills at most half the SMs become two single-tile CTAs each.  A CTA with
+  // one query tile runs a shorter period per key tile than one with two (2761 against 3234 cycles),
+  // every row is computed exactly as before (outputs are bit-identical) and nothing is merged.
+  const bool rows_ok = rest > 0 && rest * 2 <= sms && nq > 128;
+  auto row_cut = [&] {
+    plan.items_full = static_cast<int>(items - rest);
+    plan.tail_items = static_cast<int>(rest);
+    plan.tail_ctas = static_cast<int>(rest * 2);
+    plan.tail_rows = 1;
+    return plan;
+  };
+  if (mode == 3) return rows_ok ? row_cut() : plan;
   if (mode == 2) {
-    const long long rest = items % sms;
+    if (!have_pool) return plan;
     const long long total = rest * nkv_tiles;         // key-tile iterations of the partial wave
     long long n = total / 2 < sms ? total / 2 : sms;  // spans of at least two key tiles ...
     if (n > rest * 8) n = rest * 8;                   // ... and at most 8 parts per item
@@ -307,16 +327,17 @@ FaPlan fa_plan(long long items, int nkv_tiles, int sms, bool have_pool) {
     plan.tail_ctas = static_cast<int>(n);
     return plan;
   }
-  if (items * 2 > sms) return plan;  // at least half a wave: leave it whole (see above)
+  if (items * 2 > sms) return rows_ok ? row_cut() : plan;  // at least half a wave: never cut along K/V (see above)
+  // sub-half-wave grid: K/V cut if the model says it beats both the whole item (L) and the row cut (~0.85 L)
   const double L = nkv_tiles;
+  const double other = rows_ok ? 0.85 * L : L;
   long long p = static_cast<long long>(std::sqrt(L / 2.2) + 0.5);
   const long long p_max = sms / items < 8 ? sms / items : 8;
   if (p > p_max) p = p_max;
   if (p > nkv_tiles / 4) p = nkv_tiles / 4;
-  if (p < 2) return plan;
-  if (L / p + tail_split_cost() + 2.2 * p >= L) return plan;
   const long long total = items * nkv_tiles, n = items * p;
-  if ((total + 1) * n >= 0x7fffffffll) return plan;  // the kernel's span arithmetic is 32-bit
+  if (!have_pool || p < 2 || L / p + tail_split_cost() + 2.2 * p >= other || (total + 1) * n >= 0x7fffffffll)
+    return rows_ok ? row_cut() : plan;  // (the kernel's span arithmetic is 32-bit)
   plan.items_full = 0;
   plan.tail_items = static_cast<int>(items);
   plan.tail_ctas = static_cast<int>(n);
@@ -371,11 +392,12 @@ int launch_fa(DeviceState* st, const FaCall& c, cudaStream_t stream) {
 #endif
   const uint64_t items = BH * static_cast<uint64_t>(p.q_blocks);
   if (items == 0 || items > 0x7fffffffull) return FA_ERR_BAD_SHAPE;
-  const FaPlan plan = fa_plan(static_cast<long long>(items), (c.Nkv + Cfg::kKT - 1) / Cfg::kKT, st->sm_count,
+  const FaPlan plan = fa_plan(static_cast<long long>(items), (c.Nkv + Cfg::kKT - 1) / Cfg::kKT, c.Nq, st->sm_count,
                               st->pool != nullptr);
   p.items_full = plan.items_full;
   p.tail_items = plan.tail_items;
   p.tail_ctas = plan.tail_ctas;
+  p.tail_rows = plan.tail_rows;
   p.ws = nullptr;
   p.ws_count = nullptr;
   p.pf_src[0] = static_cast<const uint4*>(c.pf_src_k);
@@ -384,7 +406,7 @@ int launch_fa(DeviceState* st, const FaCall& c, cudaStream_t stream) {
   p.pf_dst[1] = static_cast<uint4*>(c.pf_dst_v);
   p.pf_words = c.pf_bytes / 16;
   void* ws = nullptr;
-  if (plan.tail_ctas > 0) {
+  if (plan.tail_ctas > 0 && !plan.tail_rows) {
     // [counters, padded to 256 B][tail_ctas * 2 slots of (D + 2) * 256 floats]
     const size_t count_bytes = (static_cast<size_t>(plan.tail_items) * 4 + 255) & ~static_cast<size_t>(255);
     const size_t bytes = count_bytes + static_cast<size_t>(plan.tail_ctas) * 2 * (D + 2) * 256 * 4;
@@ -1280,17 +1302,18 @@ int fa_plan_segments(int B, int H, int Nq, int Nkv, int sms, int* out, int max_s
   const long long items = static_cast<long long>(B) * H * p.q_blocks;
   if (items > 0x7fffffffll) return FA_ERR_BAD_SHAPE;
   const int nkv_tiles = (Nkv + 127) / 128;
-  const FaPlan plan = fa_plan(items, nkv_tiles, sms, true);
+  const FaPlan plan = fa_plan(items, nkv_tiles, Nq, sms, true);
   p.items_full = plan.items_full;
   p.tail_items = plan.tail_items;
   p.tail_ctas = plan.tail_ctas;
+  p.tail_rows = plan.tail_rows;
   int n = 0;
   for (int cta = 0; cta < plan.items_full + plan.tail_ctas; ++cta) {
     FaSegment seg;
     for (int si = 0; fa_segment(p, nkv_tiles, cta, si, seg); ++si, ++n) {
       if (out != nullptr && n < max_segments) {
         int* row = out + static_cast<size_t>(n) * 6;
-        row[0] = cta; row[1] = seg.item; row[2] = seg.kv0; row[3] = seg.kv1; row[4] = seg.slot; row[5] = seg.tail_item;
+        row[0] = cta; row[1] = seg.item; row[2] = seg.kv0; row[3] = seg.kv1; row[4] = seg.half >= 0 ? -2 - seg.half : seg.slot; row[5] = seg.tail_item;
       }
     }
   }
@@ -1298,7 +1321,7 @@ int fa_plan_segments(int B, int H, int Nq, int Nkv, int sms, int* out, int max_s
 }
 
 int fa_set_tail_split(int mode) {
-  const int before = g_tail_split.exchange(mode < 0 ? -1 : (mode > 2 ? 2 : mode), std::memory_order_relaxed);
+  const int before = g_tail_split.exchange(mode < 0 ? -1 : (mode > 3 ? 3 : mode), std::memory_order_relaxed);
   return before;
 }
 

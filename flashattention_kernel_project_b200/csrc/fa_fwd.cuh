@@ -55,6 +55,7 @@ struct FaParams {
   int items_full;
   int tail_items;
   int tail_ctas;
+  int tail_rows;           // 1: the tail is cut along QUERY ROWS instead -- two CTAs per item, one 128-row tile each, no merge
   float* ws;               // tail_ctas * 2 slots of (D + 2) * 256 floats: un-normalised O, row max, row sum
   unsigned int* ws_count;  // [tail_items] arrival counters, zero before the launch
   // Ring attention, fused exchange: while this launch computes on one K/V shard, the two otherwise idle warps of
@@ -156,7 +157,17 @@ struct FaSegment {
   int kv0, kv1;  // key-tile range
   int slot;      // -1 = whole item
   int tail_item; // index into ws_count (partial only)
+  int half;      // -1 = both 128-row tiles of the item; 0 / 1 = only that tile (FaParams::tail_rows), all key tiles
 };
+// first query row and number of 128-row tiles of a segment
+__device__ __forceinline__ void fa_segment_rows(const FaParams& p, const FaSegment& s, int& q0, int& ntile) {
+  q0 = (s.item % p.q_blocks) * 256;
+  ntile = (q0 + 128 < p.nq) ? 2 : 1;
+  if (s.half >= 0) {
+    q0 += s.half * 128;
+    ntile = 1;
+  }
+}
 
 // All of this is 32-bit arithmetic (a 64-bit division is a subroutine call that spills the caller's registers); the
 // host only cuts the tail when (tail_items * nkv_tiles + 1) * tail_ctas < 2^31 (fa_plan).
@@ -172,10 +183,16 @@ __host__ __device__ __forceinline__ int fa_span_owner(const FaParams& p, int nkv
 __host__ __device__ __forceinline__ bool fa_segment(const FaParams& p, int nkv_tiles, int cta, int idx, FaSegment& s) {
   if (cta < p.items_full) {
     if (idx != 0) return false;
-    s.item = cta; s.kv0 = 0; s.kv1 = nkv_tiles; s.slot = -1; s.tail_item = 0;
+    s.item = cta; s.kv0 = 0; s.kv1 = nkv_tiles; s.slot = -1; s.tail_item = 0; s.half = -1;
     return true;
   }
   const int t = cta - p.items_full;
+  s.half = -1;
+  if (p.tail_rows) {  // CTA pair (2 li, 2 li + 1) shares item li: one query tile each, nothing to merge
+    if (idx != 0) return false;
+    s.item = p.items_full + (t >> 1); s.kv0 = 0; s.kv1 = nkv_tiles; s.slot = -1; s.tail_item = t >> 1; s.half = t & 1;
+    return s.half == 0 || (s.item % p.q_blocks) * 256 + 128 < p.nq;  // a ragged last block may have no second tile
+  }
   const int a = fa_span_begin(p, nkv_tiles, t), b = fa_span_begin(p, nkv_tiles, t + 1);
   const int li = static_cast<int>(static_cast<unsigned>(a) / static_cast<unsigned>(nkv_tiles)) + idx;
   const int i0 = li * nkv_tiles;
@@ -288,8 +305,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
     FaSegment seg;
     for (int si = 0; fa_segment(p, nkv_tiles, cta, si, seg); ++si) {
       if (si > 0) fa_segment_boundary<D>(bars, warp, lane);
-      const int q0 = (seg.item % p.q_blocks) * 256;
-      const int ntile = (q0 + 128 < p.nq) ? 2 : 1;
+      int q0, ntile;
+      fa_segment_rows(p, seg, q0, ntile);
       if (i >= ntile) continue;
       const int n_it = seg.kv1 - seg.kv0;
       float m_used = -INFINITY;  // running max of (sign-folded) raw scores the exponent refers to
@@ -460,8 +477,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
         fa_segment_boundary<D>(bars, warp, lane);
       }
       const int bh = seg.item / p.q_blocks;
-      const int q0 = (seg.item % p.q_blocks) * 256;
-      const int ntile = (q0 + 128 < p.nq) ? 2 : 1;
+      int q0, ntile;
+      fa_segment_rows(p, seg, q0, ntile);
       const int n_it = seg.kv1 - seg.kv0;
 
       // j == 0: nothing to rescale (PV(0) overwrites O); the arrival only balances the barrier count
@@ -796,8 +813,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
       FaSegment seg;
       for (int si = 0; fa_segment(p, nkv_tiles, cta, si, seg); ++si) {
         if (si > 0) fa_segment_boundary<D>(bars, warp, lane);
-        const int q0 = (seg.item % p.q_blocks) * 256;
-        const int ntile = (q0 + 128 < p.nq) ? 2 : 1;
+        int q0, ntile;
+        fa_segment_rows(p, seg, q0, ntile);
         const int n_it = seg.kv1 - seg.kv0;
 
         // prologue: S_i(0) = Q_i K(0)^T
@@ -850,8 +867,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ 
       for (int si = 0; fa_segment(p, nkv_tiles, cta, si, seg); ++si) {
         if (si > 0) fa_segment_boundary<D>(bars, warp, lane);
         const int bh = seg.item / p.q_blocks;
-        const int q0 = (seg.item % p.q_blocks) * 256;
-        const int ntile = (q0 + 128 < p.nq) ? 2 : 1;
+        int q0, ntile;
+        fa_segment_rows(p, seg, q0, ntile);
         auto load_tile = [&](const CUtensorMap* map, uint8_t* dst, uint64_t* bar, int row0, uint64_t hint) {
           if (elect_one()) {
             mbar_arrive_expect_tx(bar, Cfg::kTileBytes);

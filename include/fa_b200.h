@@ -290,10 +290,15 @@ unsigned long long fa_launch_count(void);
  * here an ITEM is one 256-row query block of one (b,h), CTAs of the full waves own one item each, and the items of
  * the partial last wave are cut along K/V into equal spans of 128-key tiles, one CTA per span ("stream-K" tail; the
  * parts of an item are merged with the (m, l, O) rule of Streaming_FlashAttention_Forward_Kernel/flashattn_streaming_16x16.cu:247-261).
- * Writes up to max_segments rows {cta, item, kv_tile_begin, kv_tile_end, slot, tail_item} (slot -1 = whole item)
- * into `out` (may be NULL) and returns the number of segments, or a negative FA_ERR_*.
- * Environment FA_TAIL_SPLIT (read once): 0 never cuts, 1 (default) cuts where measurements say it pays (grids that
- * fill less than half the SMs), 2 cuts the partial last wave of any grid.  fa_set_tail_split(0 / 1 / 2) overrides the
+ * A last wave that fills at most half the SMs can instead be cut along QUERY ROWS: two CTAs per item, one 128-row
+ * tile each, every row computed exactly as in the whole item and nothing to merge (the reference's own grid has one
+ * CTA per 64-row block, flashattn_forward_wmma_v4.cu:452).
+ * Writes up to max_segments rows {cta, item, kv_tile_begin, kv_tile_end, slot, tail_item} into `out` (may be NULL)
+ * and returns the number of segments, or a negative FA_ERR_*.  slot: -1 = whole item; 0 / 1 = a K/V part (which of
+ * the CTA's two workspace slots holds it); -2 / -3 = rows [0,128) / [128,256) of the item against all its key tiles.
+ * Environment FA_TAIL_SPLIT (read once): 0 never cuts, 1 (default) cuts where measurements say it pays (K/V cut for
+ * grids that fill less than half the SMs, row cut for small last waves), 2 cuts the partial last wave of any grid
+ * along K/V, 3 applies only the row cut.  fa_set_tail_split(0 ... 3) overrides the
  * environment for the process, fa_set_tail_split(-1) hands the decision back to it; the previous setting is returned.  A cut item
  * is summed in a different order than a whole one (its parts are merged with the (m, l, O) rule), so a (b,h) slice
  * is bit-identical to the same slice of a larger batch only when both are decomposed alike -- e.g. with the cut off.

@@ -193,6 +193,43 @@ def test_cut_items_match_whole_items(fa, oracle):
         _check(oracle, cut32.cpu().numpy().reshape(B * H, N, D), ref, rel_tol=5e-4)
 
 
+def test_row_cut_is_bit_identical_to_whole_items(fa):
+    """The row cut (fa_plan: the items of a last wave that fills at most half the SMs become two single-tile CTAs)
+    changes only which CTA computes a query row, never how: fp16 output, fp32 output and the carried ring state must be
+    bit-identical to the uncut launch -- on whole and ragged query blocks (a last block with one tile leaves its second
+    CTA without work), partial key tiles, Nq != Nkv, both head dims, sub-wave and multi-wave grids.  (The reference's
+    grid already has one CTA per 64-row block, flashattn_forward_wmma_v4.cu:452: rows never interact.)"""
+    lib = fa.load_library()
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    shapes = [(1, 8, 1024, 1024, 64), (1, 2, 777, 777, 128), (1, 3, 300, 1000, 64), (1, 32, 4096, 4096, 128),
+              (2, 5, 1500, 700, 128), (1, 160, 384, 384, 64)]
+    for (B, H, Nq, Nkv, D) in shapes:
+        q = torch.from_numpy(_inputs(B, H, Nq, D, dist="normal", seed=Nq, std=1.5)[0]).cuda()
+        k, v = (torch.from_numpy(x).cuda() for x in _inputs(B, H, Nkv, D, dist="normal", seed=Nkv + 1, std=1.5)[1:])
+        scale = 1.0 / np.sqrt(D)
+        res = {}
+        before = lib.fa_set_tail_split(0)
+        try:
+            for mode in (0, 3):
+                lib.fa_set_tail_split(mode)
+                n = lib.fa_plan_segments(B, H, Nq, Nkv, sms, None, 0)
+                cross = fa.fa_forward_cross(q, k, v, scale) if Nq != Nkv else fa.fa_forward(q, k, v, scale)
+                f32 = fa.fa_forward_f32out(q, k, v, scale) if Nq == Nkv else None
+                # two ring steps over the halves of K/V: the second one loads the carried state (TMA) and emits fp16
+                acc = torch.full((B, H, Nq, D), float("nan"), device="cuda")
+                m, l = torch.empty((B, H, Nq), device="cuda"), torch.empty((B, H, Nq), device="cuda")
+                h = (Nkv // 2 + 7) // 8 * 8
+                fa.fa_forward_partial(q, k[:, :, :h].contiguous(), v[:, :, :h].contiguous(), acc, m, l, scale, True, False)
+                fin = fa.fa_forward_partial(q, k[:, :, h:].contiguous(), v[:, :, h:].contiguous(), acc, m, l, scale, False, True)
+                torch.cuda.synchronize()
+                res[mode] = (n, cross, f32, acc, m, l, fin)
+        finally:
+            lib.fa_set_tail_split(before)
+        assert res[3][0] > res[0][0], f"{(B, H, Nq, Nkv, D)} was meant to exercise the row cut"
+        for a, b in zip(res[0][1:], res[3][1:]):
+            assert (a is None and b is None) or torch.equal(a, b)
+
+
 def test_cut_is_deterministic_under_concurrency(fa):
     """The merge of a cut item is done by whichever CTA arrives last; it reduces the parts in span order, so the result
     must not depend on which one that is: repeated launches, overlapping on two streams (each launch owns its
