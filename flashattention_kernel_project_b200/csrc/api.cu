@@ -729,10 +729,24 @@ int host_chunk_limit() {
   }();
   return limit;
 }
-// Chunks of >= 32 MB of traffic each (8 MB per copy with four tensors: below that the per-copy cost shows, most of
-// all when 8 ranks share one host), at most host_chunk_limit() and at most one per unit.
-int host_chunks(size_t total_bytes, long long units) {
-  long long n = static_cast<long long>(total_bytes >> 25);
+// As many chunks as host_chunk_limit() allows (16) while a copy stays at least FA_HOST_CHUNK_MB (default 2) MB of one
+// tensor, at most one per unit.  Measured on 8xB200, head shards of BASELINE config 3, settings interleaved in one job
+// (scripts/e2e_chunk_sweep.py; ms per call by number of chunks):
+//   1 GPU, 256 MB per tensor:  8 chunks 16.20, 16 chunks 16.31, 32 / 64 chunks 17.06
+//   2 GPUs, 128 MB:            4 chunks 9.12, 8 chunks 8.99, 16 chunks 9.11, 64 chunks 9.77
+//   4 GPUs, 64 MB:             2 chunks 10.37, 4 chunks 9.98, 8 chunks 9.70, 16 chunks 9.40
+//   8 GPUs, 32 MB:             1 chunk 7.18, 2 chunks 6.96, 8 chunks 6.80, 16 chunks 6.39
+// The ranks of a job run in lockstep, so with few chunks every rank copies in the same direction at the same time
+// and the host's other direction idles; 8-16 chunks interleave the directions, 64 pay per-copy cost.
+int host_chunk_min_bytes_log2() {  // read per call: a tuning script changes it between calls (scripts/e2e_chunk_sweep.py)
+  const char* e = std::getenv("FA_HOST_CHUNK_MB");
+  const int mb = e != nullptr ? std::atoi(e) : 2;
+  int s = 20;
+  while ((1 << (s - 20)) < mb && s < 30) ++s;
+  return s;
+}
+int host_chunks(size_t tensor_bytes, long long units) {
+  long long n = static_cast<long long>(tensor_bytes >> host_chunk_min_bytes_log2());
   if (n > host_chunk_limit()) n = host_chunk_limit();
   if (n > units) n = units;
   return n < 1 ? 1 : static_cast<int>(n);

@@ -257,9 +257,10 @@ int fa_forward_unfused(const void* Q, const void* K, const void* V, float* O, fl
  * e.g. flashattn_streaming_16x32_2warp_softmax_v12i.cu:325-368) behind one call.  All pointers
  * are HOST pointers (pinned memory makes the copies asynchronous); device scratch is cached
  * inside the library per device and grown on demand.  The call returns after the result is in
- * the host buffer.  The batch is cut into up to 16 chunks of independent units whose H2D copy, kernel and D2H
- * copy overlap on three internal streams (environment FA_HOST_CHUNKS = 1..64 overrides the bound; config 3 measures
- * 16.2-17.1 ms for 4..64 chunks, i.e. the call is bound by the 805 MB host-to-device copy).  Calls on one device are serialised (they share the scratch);
+ * the host buffer.  The batch is cut into up to 16 chunks of independent units (copies of at least 2 MB) whose H2D
+ * copy, kernel and D2H copy overlap on three internal streams (environment FA_HOST_CHUNKS = 1..64 overrides the
+ * bound, FA_HOST_CHUNK_MB the smallest copy; config 3 measures 16.2-17.1 ms for 8..64 chunks on one GPU, i.e. the call
+ * is bound by the 805 MB host-to-device copy).  Calls on one device are serialised (they share the scratch);
  * calls on different devices run concurrently.  fa_host_release() frees the cached scratch of the current device.
  */
 int fa_forward_host(const void* Q, const void* K, const void* V, void* O, int B, int H, int N, int D,
