@@ -150,8 +150,8 @@ static_assert(kSplitGroups >= 1 && kSplitGroups <= 7, "first publication covers 
 // epilogue.  A partial one parks its un-normalised (O, m, l) in workspace slot `slot` of its CTA (0: the span starts
 // inside this item, 1: it started in an earlier item) and bumps the item's counter; the CTA that arrives last merges
 // all parts in span order (deterministic whichever CTA that is) and writes the output.  This is the "stream-K" cut
-// of the LAST WAVE only: 512 items on 148 SMs take 3.46 item-times instead of 4, which is what head-sharding
-// BASELINE config 3 over 8 GPUs (32 (b,h) per GPU) needs to scale.
+// of the partial LAST WAVE; the host (api.cu, fa_plan) applies it only where it measured faster -- grids that fill
+// less than half the SMs -- and otherwise cuts a small last wave along query rows (`half`), or not at all.
 struct FaSegment {
   int item;      // global item index = bh * q_blocks + qblk
   int kv0, kv1;  // key-tile range
